@@ -1,0 +1,88 @@
+"""Functional entry points used by the model zoo.
+
+Each function has exactly two implementations:
+
+* the sm_100a path in :mod:`..ops.cuda_ops` (hand-written kernels from
+  ``csrc/``), selected when the tensors live on a CUDA device and the fast
+  path is enabled (default on a B200);
+* the ATen composition below, used on CPU (tests, plumbing runs) and as the
+  numerical oracle for the kernels.
+
+There is no third backend and no tracing compiler in between.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_FAST = {"enabled": os.environ.get("FEDB200_FAST", "1") != "0"}
+
+
+def set_fast_path(flag: bool) -> None:
+    """Globally enable/disable the hand-written CUDA path (CUDA tensors only)."""
+    _FAST["enabled"] = bool(flag)
+
+
+def fast_path_enabled() -> bool:
+    return _FAST["enabled"]
+
+
+def _use_fast(x: torch.Tensor) -> bool:
+    return _FAST["enabled"] and x.is_cuda
+
+
+def conv_bn_act(
+    x: torch.Tensor,
+    conv: nn.Conv2d,
+    bn: nn.BatchNorm2d,
+    residual: Optional[torch.Tensor] = None,
+    act: bool = True,
+) -> torch.Tensor:
+    """``ELU?( BN_train(conv(x)) (+ residual) )`` — one ResNet group.
+
+    Semantics follow /root/reference/src/simple_models.py:149-154: batch
+    statistics are used (and running statistics updated) whenever the module
+    is in training mode, which in the reference is *always* (SURVEY Q4).
+    """
+    if _use_fast(x):
+        from . import cuda_ops
+
+        if cuda_ops.conv_bn_act_supported(x, conv, bn):
+            return cuda_ops.conv_bn_act(x, conv, bn, residual, act)
+    y = F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    y = bn(y)
+    if residual is not None:
+        y = y + residual
+    return F.elu(y) if act else y
+
+
+def pool_linear(x: torch.Tensor, linear: nn.Linear, window: int = 4) -> torch.Tensor:
+    """``linear(flatten(avg_pool2d(x, window)))`` (simple_models.py:213-215)."""
+    if _use_fast(x):
+        from . import cuda_ops
+
+        if cuda_ops.pool_linear_supported(x, linear, window):
+            return cuda_ops.pool_linear(x, linear, window)
+    y = F.avg_pool2d(x, window)
+    return F.linear(y.reshape(y.shape[0], -1), linear.weight, linear.bias)
+
+
+def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor:
+    """``ELU?(conv(x))`` for the bias-carrying convs / transposed convs of the VAE and CPC nets."""
+    y = conv(x)
+    return F.elu(y) if act else y
+
+
+def linear_act(x: torch.Tensor, linear: nn.Linear, act: bool = True) -> torch.Tensor:
+    """``ELU?(x @ W^T + b)``; on B200 the skinny GEMM + bias + ELU epilogue is one tcgen05 kernel."""
+    if _use_fast(x):
+        from . import cuda_ops
+
+        if cuda_ops.linear_act_supported(x, linear):
+            return cuda_ops.linear_act(x, linear, act)
+    y = F.linear(x, linear.weight, linear.bias)
+    return F.elu(y) if act else y
