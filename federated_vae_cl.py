@@ -1,0 +1,7 @@
+#!/usr/bin/env python
+"""`python federated_vae_cl.py [--K 8 --use_resnet ...]` — same script name as the reference; see
+federated_pytorch_test_b200/api/federated_vae_cl.py for the implementation and knob list."""
+from federated_pytorch_test_b200.api.federated_vae_cl import main
+
+if __name__ == "__main__":
+    main()
