@@ -402,7 +402,7 @@ class LBFGSNew(Optimizer):
         state.setdefault("n_iter", 0)
 
         orig_loss = closure()
-        loss = float(orig_loss)
+        loss = float(orig_loss.detach()) if torch.is_tensor(orig_loss) else float(orig_loss)
         evals_here = 1
         state["func_evals"] += 1
 
