@@ -1,0 +1,170 @@
+"""Run the UNMODIFIED reference scripts offline and time them.
+
+The reference (``baseline/_ref/src/*.py``, a verbatim copy of /root/reference made by
+``baseline/install_reference.sh``) cannot run without a network: it downloads CIFAR10 through
+torchvision and has no timers.  This shim
+
+1. replaces ``torchvision.datasets.CIFAR10`` *in memory* by a synthetic dataset with the same
+   constructor signature and item contract (uint8 HWC image -> PIL -> the script's own transform),
+2. overrides module-level constants of the script by regex on the source text (the reference's own
+   "config system": constants edited by hand), nothing else is touched,
+3. ``exec``s the script and observes it from outside: ``torch.optim.Adam.step`` is wrapped to count
+   optimizer steps, record CUDA events at the warm-up / end boundaries and stop the run.
+
+Everything on the timed path — the models, the DataLoader with its worker process, ``.to(device)``,
+closures, Adam, the diagnostics forward and ``.item()`` — is the reference's own code.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import sys
+import time
+from typing import Dict, Optional
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SRC = os.path.join(HERE, "_ref", "src")
+
+
+class _StopBench(Exception):
+    pass
+
+
+def _install_synthetic_cifar(seed: int = 1234) -> None:
+    import numpy as np
+    import torchvision
+    from PIL import Image
+
+    sys.path.insert(0, os.path.dirname(HERE))
+    from federated_pytorch_test_b200.data.cifar import make_synthetic_cifar
+
+    cache: Dict[bool, tuple] = {}
+
+    class SyntheticCIFAR10(torch.utils.data.Dataset):
+        def __init__(self, root=None, train=True, transform=None, target_transform=None, download=False):
+            if train not in cache:
+                imgs, labs = make_synthetic_cifar(train, seed)
+                cache[train] = (imgs.numpy(), labs.tolist())
+            self.data, self.targets = cache[train]
+            self.transform, self.target_transform = transform, target_transform
+
+        def __len__(self):
+            return len(self.targets)
+
+        def __getitem__(self, i):
+            img, target = Image.fromarray(self.data[i]), self.targets[i]
+            if self.transform is not None:
+                img = self.transform(img)
+            if self.target_transform is not None:
+                target = self.target_transform(target)
+            return img, target
+
+    torchvision.datasets.CIFAR10 = SyntheticCIFAR10
+
+
+def _override(src: str, consts: Dict[str, object]) -> str:
+    for name, val in consts.items():
+        src, n = re.subn(r"(?m)^%s\s*=.*$" % re.escape(name), "%s=%r" % (name, val), src, count=1)
+        if n != 1:
+            raise RuntimeError("constant %s not found in the reference script" % name)
+    return src
+
+
+def run_reference_script(script: str, consts: Dict[str, object], steps: Optional[int] = None, warmup: int = 0,
+                         workdir: Optional[str] = None) -> Dict:
+    """Execute ``baseline/_ref/src/<script>``; if ``steps`` is given stop after ``warmup+steps`` Adam steps."""
+    path = os.path.join(REF_SRC, script)
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    _install_synthetic_cifar()
+    src = _override(open(path).read(), consts)
+    sys.path.insert(0, REF_SRC)
+    cuda = torch.cuda.is_available()
+    state = {"n": 0, "ev0": None, "ev1": None, "t0": 0.0, "t1": 0.0}
+    orig_step = torch.optim.Adam.step
+
+    def counted_step(self, closure=None):
+        if steps is not None and state["n"] == warmup:
+            if cuda:
+                torch.cuda.synchronize()
+                state["ev0"] = torch.cuda.Event(enable_timing=True)
+                state["ev0"].record()
+            state["t0"] = time.perf_counter()
+        out = orig_step(self, closure)
+        state["n"] += 1
+        return out
+
+    # the diagnostics forward + .item() follow each step inside the script; stop at the START of step warmup+steps
+    def stopping_step(self, closure=None):
+        if steps is not None and state["n"] == warmup + steps:
+            if cuda:
+                state["ev1"] = torch.cuda.Event(enable_timing=True)
+                state["ev1"].record()
+                torch.cuda.synchronize()
+            state["t1"] = time.perf_counter()
+            raise _StopBench()
+        return counted_step(self, closure)
+
+    torch.optim.Adam.step = stopping_step
+    cwd = os.getcwd()
+    if workdir:
+        os.makedirs(workdir, exist_ok=True)
+        os.chdir(workdir)
+    try:
+        exec(compile(src, script, "exec"), {"__name__": "__main__"})
+    except _StopBench:
+        pass
+    finally:
+        torch.optim.Adam.step = orig_step
+        os.chdir(cwd)
+    res = {"optimizer_steps": state["n"]}
+    if steps is not None and state["ev0"] is not None and state["ev1"] is not None:
+        res["device_ms"] = state["ev0"].elapsed_time(state["ev1"])
+    if steps is not None:
+        res["wall_ms"] = (state["t1"] - state["t0"]) * 1e3
+    return res
+
+
+def run_reference_bench(gpus: int, steps: int, warmup: int) -> Dict:
+    """``bench.py --impl reference``: federated_multi.py, ResNet18, K = gpus workers — all on ONE device,
+    visited sequentially, which is what the reference does on any box.  One benchmark *step* = one
+    minibatch on every worker = ``gpus`` optimizer steps of 128 images."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return {}
+    if not os.path.exists(os.path.join(REF_SRC, "federated_multi.py")):
+        return {"impl": "reference", "unavailable": "baseline/_ref missing: run baseline/install_reference.sh (copies /root/reference; it has no setup.py to pip-install)"}
+    if not torch.cuda.is_available():
+        return {"impl": "reference", "unavailable": "no CUDA device"}
+    consts = dict(K=gpus, Nloop=1000, Nadmm=3, Nepoch=1, use_resnet=True, check_results=False, save_model=False,
+                  be_verbose=False, load_model=False)
+    from bench import ClockSampler  # same clock sampling as the product arm
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    res = run_reference_script("federated_multi.py", consts, steps=steps * gpus, warmup=warmup * gpus, workdir="/tmp/fedref_run")
+    clocks = sampler.stop()
+    ms = max(res.get("device_ms", 0.0), res.get("wall_ms", 0.0))
+    images = 128 * gpus * steps
+    value = images / (ms / 1e3)
+    return {
+        "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32 storage, tf32 conv (PyTorch defaults)", "data": "synthetic", "impl": "reference",
+        "config": {"model": "ResNet18", "algo": "fedavg", "global_batch": 128 * gpus, "K": gpus,
+                   "parallelism": "reference: K=%d replicas sequential on ONE GPU (no distributed runtime)" % gpus,
+                   "script": "baseline/_ref/src/federated_multi.py (unmodified; constants overridden by regex; synthetic CIFAR10 class)",
+                   "timing": "CUDA events around optimizer steps %d..%d, observed via a wrapper on torch.optim.Adam.step" % (warmup * gpus, (warmup + steps) * gpus),
+                   "device_ms": res.get("device_ms"), "wall_ms": res.get("wall_ms")},
+        "clocks": clocks,
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": gpus * (128 * 3 * 32 * 32 * 4 + 128 * 8),
+                "d2h_bytes_per_step": gpus * 4, "note": "the reference's only path is end to end (DataLoader -> .to(device) -> step -> .item())"},
+        "gpu_launches": 0,
+    }
+
+
+if __name__ == "__main__":
+    print(json.dumps(run_reference_bench(int(sys.argv[1]) if len(sys.argv) > 1 else 1, 5, 3)))

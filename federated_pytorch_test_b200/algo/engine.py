@@ -156,6 +156,9 @@ class Engine:
         self._adam_cache: Dict = {}
         self.stop_requested = False
         self.step_hook: Optional[Callable[["Engine"], None]] = None
+        self.last_loss1: Optional[torch.Tensor] = None
+        self.graph_replays = 0
+        self.graph_kernel_launches = 0
 
     # ------------------------------------------------------------------
     def log(self, msg: str, root_only: bool = False) -> None:
@@ -208,7 +211,7 @@ class Engine:
                 if loss.requires_grad:
                     loss.backward()
                     if has_pen:
-                        g.copy_(flatops.penalty_grad(x, g, pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2))
+                        flatops.add_penalty_grad_(g, x, pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2)
                 total = loss.detach()
                 if pre_loss[0] is None:
                     pre_loss[0] = total
@@ -231,6 +234,8 @@ class Engine:
                 if self.stop_requested:
                     break
                 self._run_visit(nloop, visit)
+            if self.stop_requested:
+                break
         self.log("Finished Training", root_only=True)
         return {"images_seen": self.images_seen, "steps": self.steps_done, "wall_s": time.time() - t0}
 
@@ -270,6 +275,7 @@ class Engine:
                 else:
                     loss1 = self._train_step(rep, opt, visit, batch, pen)
             running = loss1 if running is None else running + loss1
+            self.last_loss1 = loss1
             self.images_seen += task.batch_size_of(batch)
             self.steps_done += 1
             task.after_minibatch(rep, visit, batch, i, epoch, nloop, N, loss1, self)

@@ -1,0 +1,88 @@
+"""CUDA-graph capture of the per-minibatch Adam step (SURVEY §7.1 ``sched/``, G-launch-bound).
+
+The reference's hot loop issues ~400 eager kernel launches per minibatch (forward,
+backward, foreach-Adam, a second diagnostics forward) plus a ``.item()`` host sync
+(/root/reference/src/federated_multi.py:178-197).  Here the whole step
+
+    zero block gradient -> forward -> loss -> backward -> fused Adam(+penalty) -> diagnostics forward
+
+is captured ONCE per (replica, block, batch shape) into a ``torch.cuda.CUDAGraph`` on
+static input buffers and replayed with one launch per minibatch.  Everything that
+varies between minibatches lives in device memory (inputs, Adam step counter,
+consensus vectors), so the graph never needs re-capture inside a block visit; across
+visits the optimizer buffers persist (``BlockAdam.reset``) and so do the graphs.
+
+No tracing compiler is involved: the graph is just the recorded launch sequence of
+the hand-written kernels (and the few ATen ops that remain).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from ..ops import cuda_ops
+from ..optim.block_adam import BlockAdam
+
+
+class GraphedAdamStep:
+    WARMUP = 3
+
+    def __init__(self, engine, rep, opt: BlockAdam, visit, batch, pen):
+        self.engine, self.rep, self.opt, self.visit = engine, rep, opt, visit
+        self.static = [t.clone() if torch.is_tensor(t) else t for t in batch]
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss_out: Optional[torch.Tensor] = None
+        self.calls = 0
+        self.kernels_per_replay = 0
+        self.pen_key = None
+        self.stream = torch.cuda.Stream(device=rep.device)
+
+    # the step body; must not touch the host
+    def _body(self) -> torch.Tensor:
+        task, rep, opt = self.engine.task, self.rep, self.opt
+        opt.zero_grad()
+        loss = task.loss(rep, self.static)
+        loss.backward()
+        opt.apply_update()
+        if self.engine.cfg.diagnostics == "post":
+            with torch.no_grad():
+                return task.loss(rep, self.static).detach()
+        return loss.detach()
+
+    def _pen_key(self, pen):
+        return (pen.z.data_ptr() if pen.z is not None else 0, pen.y.data_ptr() if pen.y is not None else 0,
+                float(pen.rho), self.visit.lambda1, self.visit.lambda2)
+
+    def _capture(self) -> None:
+        before = cuda_ops.launch_count()
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=self.stream):
+            self.loss_out = self._body()
+        self.graph = g
+        self.kernels_per_replay = cuda_ops.launch_count() - before
+
+    def run(self, batch, pen) -> torch.Tensor:
+        opt = self.opt
+        key = self._pen_key(pen)
+        if key != self.pen_key:          # consensus buffers changed (new block visit): the graph bakes their addresses
+            self.pen_key = key
+            self.graph = None
+            self.calls = 0
+        opt.set_penalty(pen.z, pen.y, pen.rho, self.visit.lambda1, self.visit.lambda2)
+        for dst, src in zip(self.static, batch):
+            if torch.is_tensor(dst):
+                if dst.shape != src.shape:
+                    raise RuntimeError("graphed step called with a different batch shape")
+                dst.copy_(src, non_blocking=True)
+        self.calls += 1
+        if self.graph is None:
+            if self.calls <= self.WARMUP:
+                return self._body().clone()   # eager warm-up (lazy inits, cudaFuncSetAttribute, autotune)
+            self._capture()
+            # the capture itself does not execute: replay once for this minibatch
+        self.graph.replay()
+        self.engine.graph_replays += 1
+        self.engine.graph_kernel_launches += self.kernels_per_replay
+        return self.loss_out.clone()

@@ -129,7 +129,7 @@ class ADMM(Strategy):
 
     def begin_block(self, ci: int, N: int, xs: List[torch.Tensor]) -> None:
         super().begin_block(ci, N, xs)
-        self.ys = [torch.zeros_like(x) for x in xs]
+        self.ys = [self.coll.zeros_like_block(x, "y") for x in xs]
         if self.bb.enabled:
             self.yhat0 = [x.clone() if self.bb.seed_yhat0_with_x else torch.zeros_like(x) for x in xs]
             self.x0 = [torch.zeros_like(x) for x in xs]

@@ -1,0 +1,308 @@
+// Torch glue for the sm_100a kernels: tensor checks, stream selection, pybind.  All math lives in the .cu files.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "fedb200.h"
+
+namespace fb = fedb200;
+using torch::Tensor;
+
+static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+static const float* fptr(const Tensor& t) { return t.data_ptr<float>(); }
+static float* fptr_mut(Tensor& t) { return t.data_ptr<float>(); }
+static const float* opt_ptr(const c10::optional<Tensor>& t) { return (t.has_value() && t->defined()) ? t->data_ptr<float>() : nullptr; }
+
+#define CHECK_F32_CUDA(x) TORCH_CHECK((x).is_cuda() && (x).scalar_type() == torch::kFloat32, #x " must be a CUDA float32 tensor")
+#define CHECK_CONTIG(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+
+// ---------------------------------------------------------------------------------------------- flat ops
+void adam_prox(Tensor x, Tensor g, Tensor m, Tensor v, Tensor step, double lr, double b1, double b2, double eps,
+               c10::optional<Tensor> z, c10::optional<Tensor> y, double rho, double l1, double l2) {
+  CHECK_F32_CUDA(x); CHECK_CONTIG(x); CHECK_CONTIG(g); CHECK_CONTIG(m); CHECK_CONTIG(v);
+  c10::cuda::CUDAGuard guard(x.device());
+  fb::adam_prox(fptr_mut(x), fptr(g), fptr_mut(m), fptr_mut(v), step.data_ptr<int>(), (int)x.numel(), (float)lr, (float)b1,
+                (float)b2, (float)eps, opt_ptr(z), opt_ptr(y), (float)rho, (float)l1, (float)l2, cur_stream());
+}
+void bump_step(Tensor step) {
+  c10::cuda::CUDAGuard guard(step.device());
+  fb::bump_step(step.data_ptr<int>(), cur_stream());
+}
+Tensor l1_l2(Tensor g) {
+  CHECK_F32_CUDA(g); CHECK_CONTIG(g);
+  c10::cuda::CUDAGuard guard(g.device());
+  auto out = torch::empty({2}, g.options());
+  fb::l1_l2(fptr(g), (int)g.numel(), fptr_mut(out), cur_stream());
+  return out;
+}
+std::vector<Tensor> make_pair(Tensor g, Tensor gprev, Tensor d, double t, double trust) {
+  CHECK_F32_CUDA(g); CHECK_CONTIG(g); CHECK_CONTIG(gprev); CHECK_CONTIG(d);
+  c10::cuda::CUDAGuard guard(g.device());
+  auto y = torch::empty_like(g), s = torch::empty_like(g);
+  auto out = torch::empty({3}, g.options());
+  fb::make_pair(fptr(g), fptr(gprev), fptr(d), (float)t, (float)trust, fptr_mut(y), fptr_mut(s), (int)g.numel(), fptr_mut(out), cur_stream());
+  return {y, s, out};
+}
+Tensor welford(Tensor g, Tensor mean, Tensor m2, int64_t n_iter) {
+  CHECK_F32_CUDA(g);
+  c10::cuda::CUDAGuard guard(g.device());
+  auto out = torch::empty({1}, g.options());
+  fb::welford(fptr(g), fptr_mut(mean), fptr_mut(m2), (int)g.numel(), 1.0f / (float)n_iter, fptr_mut(out), cur_stream());
+  return out;
+}
+Tensor penalty_value(Tensor x, c10::optional<Tensor> z, c10::optional<Tensor> y, double rho, double l1, double l2) {
+  CHECK_F32_CUDA(x); CHECK_CONTIG(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = torch::empty({1}, x.options());
+  fb::penalty_value(fptr(x), opt_ptr(z), opt_ptr(y), (float)rho, (float)l1, (float)l2, (int)x.numel(), fptr_mut(out), cur_stream());
+  return out;
+}
+void penalty_grad(Tensor g, Tensor x, c10::optional<Tensor> z, c10::optional<Tensor> y, double rho, double l1, double l2) {
+  CHECK_F32_CUDA(g); CHECK_CONTIG(g); CHECK_CONTIG(x);
+  c10::cuda::CUDAGuard guard(g.device());
+  fb::penalty_grad(fptr_mut(g), fptr(x), opt_ptr(z), opt_ptr(y), (float)rho, (float)l1, (float)l2, (int)g.numel(), cur_stream());
+}
+Tensor multi_dot(std::vector<Tensor> a, std::vector<Tensor> b) {
+  TORCH_CHECK(a.size() == b.size() && !a.empty() && a.size() <= 8, "multi_dot: 1..8 pairs");
+  c10::cuda::CUDAGuard guard(a[0].device());
+  std::vector<const float*> pa, pb;
+  for (size_t i = 0; i < a.size(); ++i) {
+    CHECK_F32_CUDA(a[i]); CHECK_CONTIG(a[i]); CHECK_CONTIG(b[i]);
+    TORCH_CHECK(a[i].numel() == a[0].numel() && b[i].numel() == a[0].numel(), "multi_dot: equal lengths required");
+    pa.push_back(fptr(a[i])); pb.push_back(fptr(b[i]));
+  }
+  auto out = torch::empty({(int64_t)a.size()}, a[0].options());
+  fb::multi_dot(pa.data(), pb.data(), (int)a.size(), (int)a[0].numel(), fptr_mut(out), cur_stream());
+  return out;
+}
+Tensor lbfgs_two_loop(Tensor Y, Tensor S, Tensor order, Tensor g, double hdiag) {
+  CHECK_F32_CUDA(Y); CHECK_CONTIG(Y); CHECK_CONTIG(S); CHECK_CONTIG(g);
+  TORCH_CHECK(order.scalar_type() == torch::kInt32 && order.is_cuda(), "order must be a CUDA int32 tensor");
+  c10::cuda::CUDAGuard guard(g.device());
+  const int k = (int)order.numel(), n = (int)g.numel();
+  auto d = torch::empty_like(g);
+  auto work = torch::empty({(int64_t)fb::lbfgs_two_loop_work_floats(k)}, g.options());
+  fb::lbfgs_two_loop(fptr(Y), fptr(S), order.data_ptr<int>(), k, n, (int)Y.size(1), fptr(g), (float)hdiag, fptr_mut(d), fptr_mut(work), cur_stream());
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------- elementwise
+Tensor normalize_u8(Tensor u8, std::vector<double> mean, std::vector<double> stdv, int64_t c_out, bool to_nchw) {
+  TORCH_CHECK(u8.is_cuda() && u8.scalar_type() == torch::kUInt8 && u8.dim() == 4 && u8.size(3) == 3 && u8.is_contiguous(),
+              "normalize_u8 expects a contiguous CUDA uint8 [N,H,W,3] tensor");
+  c10::cuda::CUDAGuard guard(u8.device());
+  const int64_t N = u8.size(0), H = u8.size(1), W = u8.size(2);
+  float m3[3] = {(float)mean[0], (float)mean[1], (float)mean[2]}, s3[3] = {(float)stdv[0], (float)stdv[1], (float)stdv[2]};
+  auto opts = torch::TensorOptions().dtype(torch::kFloat32).device(u8.device());
+  Tensor out = to_nchw ? torch::empty({N, 3, H, W}, opts) : torch::empty({N, H, W, c_out}, opts);
+  fb::normalize_u8_nhwc(u8.data_ptr<uint8_t>(), fptr_mut(out), (int)(N * H * W), (int)c_out, m3, s3, to_nchw ? 1 : 0, (int)H, (int)W, cur_stream());
+  return out;
+}
+void col_stats(Tensor y, Tensor stats) {
+  CHECK_F32_CUDA(y); CHECK_CONTIG(y);
+  c10::cuda::CUDAGuard guard(y.device());
+  const int C = (int)y.size(-1);
+  fb::col_stats(fptr(y), fptr_mut(stats), (int)(y.numel() / C), C, cur_stream());
+}
+// y, out: [M, C] views of NHWC tensors.  Returns (out, save_mean, save_invstd).
+std::vector<Tensor> bn_elu_fwd(Tensor y, Tensor stats, Tensor gamma, Tensor beta, c10::optional<Tensor> residual,
+                               c10::optional<Tensor> running_mean, c10::optional<Tensor> running_var, double eps,
+                               double momentum, bool act) {
+  CHECK_F32_CUDA(y); CHECK_CONTIG(y);
+  c10::cuda::CUDAGuard guard(y.device());
+  const int C = (int)y.size(-1);
+  const int M = (int)(y.numel() / C);
+  auto out = torch::empty_like(y);
+  auto sm = torch::empty({C}, y.options()), si = torch::empty({C}, y.options());
+  float* rm = (running_mean.has_value() && running_mean->defined()) ? running_mean->data_ptr<float>() : nullptr;
+  float* rv = (running_var.has_value() && running_var->defined()) ? running_var->data_ptr<float>() : nullptr;
+  fb::bn_elu_fwd(fptr(y), fptr(stats), fptr(gamma), fptr(beta), opt_ptr(residual), fptr_mut(out), rm, rv, fptr_mut(sm),
+                 fptr_mut(si), M, C, (float)eps, (float)momentum, act ? 1 : 0, 1, cur_stream());
+  return {out, sm, si};
+}
+// Returns (dy, dres or undefined); accumulates into dgamma / dbeta when given.
+std::vector<Tensor> bn_elu_bwd(Tensor dout, Tensor out, Tensor y, Tensor mean, Tensor invstd, Tensor gamma,
+                               c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta, bool want_dres, bool act) {
+  CHECK_F32_CUDA(dout); CHECK_CONTIG(dout); CHECK_CONTIG(out); CHECK_CONTIG(y);
+  c10::cuda::CUDAGuard guard(y.device());
+  const int C = (int)y.size(-1);
+  const int M = (int)(y.numel() / C);
+  auto sums = torch::empty({2 * C}, y.options());
+  fb::bn_elu_bwd_reduce(fptr(dout), fptr(out), fptr(y), fptr(mean), fptr(invstd), fptr_mut(sums), M, C, act ? 1 : 0, cur_stream());
+  auto dy = torch::empty_like(y);
+  Tensor dres;
+  if (want_dres) dres = torch::empty_like(y);
+  float* dg = (dgamma.has_value() && dgamma->defined()) ? dgamma->data_ptr<float>() : nullptr;
+  float* db = (dbeta.has_value() && dbeta->defined()) ? dbeta->data_ptr<float>() : nullptr;
+  fb::bn_elu_bwd_apply(fptr(dout), fptr(out), fptr(y), fptr(mean), fptr(invstd), fptr(gamma), fptr(sums), fptr_mut(dy),
+                       want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0, cur_stream());
+  return {dy, dres};
+}
+Tensor avgpool_nhwc(Tensor x) {   // [N,H,W,C] -> [N,C]
+  CHECK_F32_CUDA(x); CHECK_CONTIG(x);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = torch::empty({x.size(0), x.size(3)}, x.options());
+  fb::avgpool_nhwc(fptr(x), fptr_mut(out), (int)x.size(0), (int)(x.size(1) * x.size(2)), (int)x.size(3), cur_stream());
+  return out;
+}
+Tensor avgpool_nhwc_bwd(Tensor dout, int64_t H, int64_t W) {
+  CHECK_F32_CUDA(dout); CHECK_CONTIG(dout);
+  c10::cuda::CUDAGuard guard(dout.device());
+  auto dx = torch::empty({dout.size(0), H, W, dout.size(1)}, dout.options());
+  fb::avgpool_nhwc_bwd(fptr(dout), fptr_mut(dx), (int)dout.size(0), (int)(H * W), (int)dout.size(1), cur_stream());
+  return dx;
+}
+Tensor weight_flip(Tensor w) {    // [Co,kh,kw,Ci] -> [Ci,kh,kw,Co], taps rotated
+  CHECK_F32_CUDA(w); CHECK_CONTIG(w);
+  c10::cuda::CUDAGuard guard(w.device());
+  auto out = torch::empty({w.size(3), w.size(1), w.size(2), w.size(0)}, w.options());
+  fb::weight_krsc_flip(fptr(w), fptr_mut(out), (int)w.size(0), (int)w.size(3), (int)w.size(1), (int)w.size(2), cur_stream());
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------- tensor cores
+Tensor linear_tf32(Tensor x, Tensor w, c10::optional<Tensor> bias, bool act) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "linear_tf32: x [M,K], w [N,K]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int M = (int)x.size(0), K = (int)x.size(1), N = (int)w.size(0);
+  auto out = torch::empty({M, N}, x.options());
+  fb::linear_tf32(fptr(x), fptr(w), opt_ptr(bias), fptr_mut(out), M, N, K, K, K, N, act ? 1 : 0, cur_stream());
+  return out;
+}
+bool conv_supported(int64_t H_out, int64_t W_out, int64_t C_in, int64_t stride) {
+  return fb::conv_geometry_supported((int)H_out, (int)W_out, (int)C_in, (int)stride);
+}
+// x: [N,H,W,Ci] contiguous; w: [Co,kh,kw,Ci] contiguous.  Returns y [N,Ho,Wo,Co]; stats (2*Co) accumulated if given.
+Tensor conv2d_nhwc(Tensor x, Tensor w, c10::optional<Tensor> stats, int64_t stride, int64_t pad, int64_t dil) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.size(3) == w.size(3), "conv2d_nhwc: x [N,H,W,Ci], w [Co,kh,kw,Ci]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), Ci = (int)x.size(3);
+  const int Co = (int)w.size(0), kh = (int)w.size(1), kw = (int)w.size(2);
+  const int Ho = (H + 2 * (int)pad - (int)dil * (kh - 1) - 1) / (int)stride + 1;
+  const int Wo = (W + 2 * (int)pad - (int)dil * (kw - 1) - 1) / (int)stride + 1;
+  auto y = torch::empty({NB, Ho, Wo, Co}, x.options());
+  float* st = (stats.has_value() && stats->defined()) ? stats->data_ptr<float>() : nullptr;
+  fb::conv2d_nhwc_tf32(fptr(x), fptr(w), fptr_mut(y), st, NB, H, W, Ci, Co, kh, kw, (int)stride, (int)pad, (int)dil, Ho, Wo, cur_stream());
+  return y;
+}
+
+// ---------------------------------------------------------------------------------------------- losses
+std::vector<Tensor> cross_entropy_fwd(Tensor logits, Tensor labels) {
+  CHECK_F32_CUDA(logits); CHECK_CONTIG(logits);
+  TORCH_CHECK(labels.scalar_type() == torch::kInt64 && labels.is_cuda(), "labels must be CUDA int64");
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto loss = torch::empty({}, logits.options());
+  auto probs = torch::empty_like(logits);
+  fb::cross_entropy_fwd(fptr(logits), (const long long*)labels.data_ptr<int64_t>(), fptr_mut(loss), fptr_mut(probs),
+                        (int)logits.size(0), (int)logits.size(1), cur_stream());
+  return {loss, probs};
+}
+Tensor cross_entropy_bwd(Tensor probs, Tensor labels, Tensor gout) {
+  c10::cuda::CUDAGuard guard(probs.device());
+  auto d = torch::empty_like(probs);
+  auto g = gout.contiguous();
+  fb::cross_entropy_bwd(fptr(probs), (const long long*)labels.data_ptr<int64_t>(), fptr(g), fptr_mut(d), (int)probs.size(0),
+                        (int)probs.size(1), cur_stream());
+  return d;
+}
+Tensor vae_loss_fwd(Tensor recon, Tensor x, Tensor mu, Tensor logvar) {
+  CHECK_F32_CUDA(recon); CHECK_CONTIG(recon); CHECK_CONTIG(x); CHECK_CONTIG(mu); CHECK_CONTIG(logvar);
+  c10::cuda::CUDAGuard guard(recon.device());
+  auto out = torch::empty({}, recon.options());
+  fb::vae_loss_fwd(fptr(recon), fptr(x), (int)recon.numel(), fptr(mu), fptr(logvar), (int)mu.numel(), fptr_mut(out), cur_stream());
+  return out;
+}
+std::vector<Tensor> vae_loss_bwd(Tensor recon, Tensor x, Tensor mu, Tensor logvar, Tensor gout) {
+  c10::cuda::CUDAGuard guard(recon.device());
+  auto dr = torch::empty_like(recon), dm = torch::empty_like(mu), dl = torch::empty_like(logvar);
+  auto g = gout.contiguous();
+  fb::vae_loss_bwd(fptr(recon), fptr(x), (int)recon.numel(), fptr(mu), fptr(logvar), (int)mu.numel(), fptr(g), fptr_mut(dr),
+                   fptr_mut(dm), fptr_mut(dl), cur_stream());
+  return {dr, dm, dl};
+}
+
+// ---------------------------------------------------------------------------------------------- collectives
+// Pointers are passed as integers: local tensors' data_ptr() or peer-mapped addresses from symmetric memory.
+void block_reduce(int64_t mode, std::vector<int64_t> x_ptrs, std::vector<int64_t> y_ptrs, std::vector<int64_t> local_idx,
+                  Tensor z, int64_t n, double inv_scale, double rho, Tensor out, std::vector<int64_t> ctrl_ptrs,
+                  Tensor sync, int64_t world, int64_t rank, int64_t mc_x, int64_t mc_y) {
+  CHECK_F32_CUDA(z); CHECK_F32_CUDA(out);
+  TORCH_CHECK(out.numel() >= 4 + fb::COMM_MAX_LOCAL, "out too small");
+  c10::cuda::CUDAGuard guard(z.device());
+  fb::CommArgs a{};
+  a.mode = (int)mode; a.K = (int)x_ptrs.size(); a.n_local = (int)local_idx.size(); a.world = (int)world; a.rank = (int)rank;
+  a.n = (int)n; a.inv_scale = (float)inv_scale; a.rho = (float)rho;
+  TORCH_CHECK(a.K <= fb::COMM_MAX_K && a.n_local <= fb::COMM_MAX_LOCAL && a.world <= fb::COMM_MAX_WORLD, "block_reduce: limits exceeded");
+  for (int k = 0; k < a.K; ++k) {
+    a.x[k] = reinterpret_cast<const float*>(x_ptrs[k]);
+    a.y[k] = y_ptrs.empty() ? nullptr : reinterpret_cast<const float*>(y_ptrs[k]);
+  }
+  for (int j = 0; j < a.n_local; ++j) {
+    a.xl[j] = reinterpret_cast<float*>(x_ptrs[local_idx[j]]);
+    a.yl[j] = y_ptrs.empty() ? nullptr : reinterpret_cast<float*>(y_ptrs[local_idx[j]]);
+  }
+  a.mc_x = reinterpret_cast<const float*>(mc_x);
+  a.mc_y = reinterpret_cast<const float*>(mc_y);
+  a.z = z.data_ptr<float>();
+  a.out = out.data_ptr<float>();
+  for (int p = 0; p < a.world && p < (int)ctrl_ptrs.size(); ++p) a.ctrl[p] = reinterpret_cast<uint32_t*>(ctrl_ptrs[p]);
+  a.sync = reinterpret_cast<uint32_t*>(sync.data_ptr<int>());
+  fb::block_reduce_launch(a, cur_stream());
+}
+
+// ---------------------------------------------------------------------------------------------- CUDA IPC helpers
+// Fallback symmetric-memory transport when torch's symmetric memory is unavailable: plain cudaMalloc'ed arenas
+// exported/imported with CUDA IPC handles (exchanged through the torch.distributed store by the Python side).
+py::bytes ipc_get_handle(int64_t ptr) {
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(ptr));
+  TORCH_CHECK(e == cudaSuccess, "cudaIpcGetMemHandle: ", cudaGetErrorString(e));
+  return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+}
+int64_t ipc_open_handle(py::bytes handle) {
+  std::string s = handle;
+  TORCH_CHECK(s.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, s.data(), sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  TORCH_CHECK(e == cudaSuccess, "cudaIpcOpenMemHandle: ", cudaGetErrorString(e));
+  return reinterpret_cast<int64_t>(p);
+}
+void ipc_close_handle(int64_t ptr) { cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr)); }
+
+int64_t launch_count() { return (int64_t)fb::launch_count(); }
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "federated_pytorch_test_b200: hand-written sm_100a kernels";
+  m.def("launch_count", &launch_count);
+  m.def("adam_prox", &adam_prox);
+  m.def("bump_step", &bump_step);
+  m.def("l1_l2", &l1_l2);
+  m.def("make_pair", &make_pair);
+  m.def("welford", &welford);
+  m.def("penalty_value", &penalty_value);
+  m.def("penalty_grad", &penalty_grad);
+  m.def("multi_dot", &multi_dot);
+  m.def("lbfgs_two_loop", &lbfgs_two_loop);
+  m.def("normalize_u8", &normalize_u8);
+  m.def("col_stats", &col_stats);
+  m.def("bn_elu_fwd", &bn_elu_fwd);
+  m.def("bn_elu_bwd", &bn_elu_bwd);
+  m.def("avgpool_nhwc", &avgpool_nhwc);
+  m.def("avgpool_nhwc_bwd", &avgpool_nhwc_bwd);
+  m.def("weight_flip", &weight_flip);
+  m.def("linear_tf32", &linear_tf32);
+  m.def("conv_supported", &conv_supported);
+  m.def("conv2d_nhwc", &conv2d_nhwc);
+  m.def("cross_entropy_fwd", &cross_entropy_fwd);
+  m.def("cross_entropy_bwd", &cross_entropy_bwd);
+  m.def("vae_loss_fwd", &vae_loss_fwd);
+  m.def("vae_loss_bwd", &vae_loss_bwd);
+  m.def("block_reduce", &block_reduce);
+  m.def("ipc_get_handle", &ipc_get_handle);
+  m.def("ipc_open_handle", &ipc_open_handle);
+  m.def("ipc_close_handle", &ipc_close_handle);
+}

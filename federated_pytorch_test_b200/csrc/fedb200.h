@@ -1,0 +1,88 @@
+// Launcher declarations shared by the .cu translation units (torch-free) and bindings.cpp (torch glue).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fedb200 {
+
+// every kernel launcher bumps this; bindings expose it so benchmarks can report `gpu_launches`
+void count_launch(int n = 1);
+long long launch_count();
+
+// ---- tcgen05 implicit GEMM (gemm_tcgen05.cu) -------------------------------------------------------
+int pick_block_n(int M, int N);
+void linear_tf32(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, int ldx, int ldw,
+                 int ldo, int act, cudaStream_t stream);
+bool conv_geometry_supported(int H_out, int W_out, int C_in, int stride);
+void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
+                      int kh, int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream);
+
+// ---- flat-vector kernels (flat_kernels.cu) ---------------------------------------------------------
+void adam_prox(float* x, const float* g, float* m, float* v, const int* step_dev, int n, float lr, float b1, float b2,
+               float eps, const float* z, const float* y, float rho, float l1, float l2, cudaStream_t s);
+void bump_step(int* step_dev, cudaStream_t s);
+void l1_l2(const float* g, int n, float* out2, cudaStream_t s);
+void make_pair(const float* g, const float* gprev, const float* d, float t, float trust, float* y, float* sv, int n,
+               float* out3, cudaStream_t s);
+void welford(const float* g, float* mean, float* m2, int n, float inv_n, float* out1, cudaStream_t s);
+void penalty_value(const float* x, const float* z, const float* y, float rho, float l1, float l2, int n, float* out1,
+                   cudaStream_t s);
+void penalty_grad(float* g, const float* x, const float* z, const float* y, float rho, float l1, float l2, int n,
+                  cudaStream_t s);
+void multi_dot(const float* const* a, const float* const* b, int npairs, int n, float* out, cudaStream_t s);
+void lbfgs_two_loop(const float* Y, const float* S, const int* order, int k, int n, int ld, const float* g, float hdiag,
+                    float* d, float* work, cudaStream_t s);
+size_t lbfgs_two_loop_work_floats(int k);
+
+// ---- elementwise / normalisation (elementwise_kernels.cu) ------------------------------------------
+void normalize_u8_nhwc(const uint8_t* in, float* out, int npix, int c_out, const float* mean3, const float* std3,
+                       int to_nchw, int H, int W, cudaStream_t s);
+void col_stats(const float* y, float* stats, int M, int C, cudaStream_t s);
+void bn_elu_fwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* residual,
+                float* out, float* running_mean, float* running_var, float* save_mean, float* save_invstd, int M, int C,
+                float eps, float momentum, int act, int training, cudaStream_t s);
+void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                       float* sums, int M, int C, int act, cudaStream_t s);
+void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                      const float* gamma, const float* sums, float* dy, float* dres, float* dgamma, float* dbeta, int M,
+                      int C, int act, cudaStream_t s);
+void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_t s);
+void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaStream_t s);
+void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, int kw, cudaStream_t s);
+
+// ---- losses (loss_kernels.cu) --------------------------------------------------------------------
+void cross_entropy_fwd(const float* logits, const long long* labels, float* loss, float* probs, int B, int C,
+                       cudaStream_t s);
+void cross_entropy_bwd(const float* probs, const long long* labels, const float* gout, float* dlogits, int B, int C,
+                       cudaStream_t s);
+void vae_loss_fwd(const float* recon, const float* x, int n, const float* mu, const float* logvar, int nl, float* out,
+                  cudaStream_t s);
+void vae_loss_bwd(const float* recon, const float* x, int n, const float* mu, const float* logvar, int nl,
+                  const float* gout, float* drecon, float* dmu, float* dlogvar, cudaStream_t s);
+
+// ---- fused block collectives (comm_kernels.cu) -------------------------------------------------------
+constexpr int COMM_MAX_K = 64;       // contributions (workers) per aggregation
+constexpr int COMM_MAX_LOCAL = 16;   // replicas hosted by one process
+constexpr int COMM_MAX_WORLD = 16;   // processes meeting through peer memory
+constexpr int COMM_THREADS = 512;
+
+struct CommArgs {
+  int mode;                          // 0 FedAvg, 1 FedProx, 2 ADMM
+  int K, n_local, world, rank;
+  int n;                             // floats in the block slice
+  float inv_scale;                   // 1/K, or 1/(K rho) for ADMM
+  float rho;
+  const float* x[COMM_MAX_K];        // x_k slices of ALL workers (local or peer-mapped pointers)
+  const float* y[COMM_MAX_K];        // y_k slices (ADMM) or nullptr
+  float* xl[COMM_MAX_LOCAL];         // this process' replicas (writable aliases of the matching x[...])
+  float* yl[COMM_MAX_LOCAL];
+  const float* mc_x;                 // multicast address of the x slice (NVLS path; requires K == world) or nullptr
+  const float* mc_y;
+  float* z;                          // local copy of the consensus vector (in/out)
+  float* out;                        // [0] dual^2, [1] primal (all workers), [2] #non-finite, [3] local primal, [4+j] per-replica sq
+  uint32_t* ctrl[COMM_MAX_WORLD];    // control pads of every rank (peer-mapped), 4 x COMM_MAX_WORLD words each
+  uint32_t* sync;                    // local: [0] = epoch of the last completed aggregation
+};
+void block_reduce_launch(const CommArgs& args, cudaStream_t s);
+
+}  // namespace fedb200

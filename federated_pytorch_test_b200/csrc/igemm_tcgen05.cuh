@@ -1,0 +1,220 @@
+// Implicit-GEMM on 5th-gen tensor cores: ONE warp-specialised kernel for
+//   (a) plain GEMM          C[M,N]   = A[M,K] * B[N,K]^T                 (Linear layers, 1x1 convs on latent grids)
+//   (b) NHWC convolution    Y[m,co]  = sum_{r,s,ci} X[n,h*st+r*d-p,w*st+s*d-p,ci] * W[co,r,s,ci]
+// A and B tiles are brought in by TMA as 128-byte-swizzled K-major tiles (32 fp32 per row); for (b) the A tile of
+// filter tap (r,s) is a 4-D TMA box over the NHWC activation [C,W,H,N] shifted by the tap offset, with out-of-bounds
+// rows/columns zero-filled by the TMA unit — the im2col matrix is never materialised.  One elected thread issues
+// tcgen05.mma.kind::tf32 into a TMEM accumulator (128 lanes x BLOCK_N columns); four epilogue warps read it back
+// with tcgen05.ld and apply the fused epilogue:
+//   * bias + ELU (dense layers), or
+//   * per-channel sum / sum-of-squares of the tile (BatchNorm batch statistics, reduced across the CTA in shared
+//     memory, one atomicAdd per channel per CTA) — SURVEY G1/G2.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), one tmem_full mbarrier (MMA -> epilogue).
+#pragma once
+#include "sm100.cuh"
+
+namespace fedb200 {
+
+constexpr int IG_BLOCK_M = 128;
+constexpr int IG_BLOCK_K = 32;  // fp32 elements per k-block = 128 B = one swizzle row
+constexpr int IG_UMMA_K = 8;    // tf32: 32 B per MMA k-step
+constexpr int IG_THREADS = 192;
+
+struct IgemmParams {
+  int M, N;              // output rows (pixels) and columns (channels)
+  int num_k_blocks;      // taps * cblocks
+  int cblocks;           // ceil(Cin / 32); k-block kb -> tap = kb / cblocks, cb = kb % cblocks
+  int taps_w;            // filter width (tap -> r = tap / taps_w, s = tap % taps_w); 1 for GEMM
+  int b_cols_per_tap;    // columns of the weight matrix per tap (= Cin as stored)
+  int is_conv;           // 0: A is a 2-D map [K, M]; 1: A is a 4-D map [C, W, H, N]
+  int HW_out, W_out;     // conv: output pixels per image, output width
+  int stride, pad, dil;  // conv geometry
+  float* out;            // [M, ldo]
+  int ldo;
+  const float* bias;     // [N] or nullptr
+  int act;               // 1 = ELU
+  float* stats;          // [2*N]: sum, sumsq per column (atomicAdd) or nullptr
+};
+
+template <int BLOCK_N, int STAGES>
+struct IgemmSmem {
+  static constexpr int A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 4;   // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * IG_BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;         // per-epilogue-warp transpose tiles
+  static constexpr int PART_BYTES = 4 * BLOCK_N * 2 * 4;        // per-warp column partials (sum, sumsq)
+  static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + PART_BYTES + BAR_BYTES + 1024;  // + align slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const IgemmParams p) {
+  using S = IgemmSmem<BLOCK_N, STAGES>;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N must be a multiple of 32 in [32,256]");
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 for 32/64/128/256
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;                                           // STAGES x [A | B], each 1024-B aligned
+  float* scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
+  float* part = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::SCRATCH_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::SCRATCH_BYTES + S::PART_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * IG_BLOCK_M;
+  const int n0 = blockIdx.y * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int img = 0, h_base = 0;
+      if (p.is_conv) {
+        img = m0 / p.HW_out;
+        h_base = (m0 % p.HW_out) / p.W_out;
+      }
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = tiles + s * S::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + S::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        const int tap = kb / p.cblocks;
+        const int cb = kb - tap * p.cblocks;
+        if (p.is_conv) {
+          const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
+          tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad,
+                      h_base * p.stride + r * p.dil - p.pad, img);
+        } else {
+          tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * IG_BLOCK_K, m0);
+        }
+        tma_load_2d(b_dst, &tmap_b, &full_bar[s], tap * p.b_cols_per_tap + cb * IG_BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BLOCK_N);
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(tiles + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+        for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+          // advance along K inside the 128-B swizzle atom: +32 B per step (encoded >>4 => +2)
+          umma_tf32(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+        if (kb == p.num_k_blocks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    float* my_scratch = scratch + (warp - 2) * 32 * 33;
+    float* my_part = part + (warp - 2) * BLOCK_N * 2;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        const int col = n0 + c0 + j;
+        if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+        if (p.act) x = elu1(x);
+        f[j] = x;
+      }
+      if (row_ok) {
+        float* dst = p.out + size_t(row) * p.ldo + n0 + c0;
+        if (n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) dst[j] = f[j];
+        }
+      }
+      if (p.stats != nullptr) {
+        // column sums over this warp's 32 rows via a padded shared-memory transpose
+#pragma unroll
+        for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = row_ok ? f[j] : 0.f;
+        __syncwarp();
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const float x = my_scratch[r * 33 + lane];
+          s1 += x;
+          s2 = fmaf(x, x, s2);
+        }
+        my_part[c0 + lane] = s1;
+        my_part[BLOCK_N + c0 + lane] = s2;
+        __syncwarp();
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      const int t = threadIdx.x - 64;
+      for (int c = t; c < BLOCK_N; c += 128) {
+        if (n0 + c < p.N) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            s1 += part[w * BLOCK_N * 2 + c];
+            s2 += part[w * BLOCK_N * 2 + BLOCK_N + c];
+          }
+          atomicAdd(p.stats + n0 + c, s1);
+          atomicAdd(p.stats + p.N + n0 + c, s2);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace fedb200

@@ -1,0 +1,321 @@
+"""Python face of the sm_100a extension (``csrc/``): thin wrappers and the
+``torch.autograd.Function``s that wire the kernels into autograd.
+
+Activation layout on this path: NHWC memory.  Tensors keep their logical NCHW
+shape with ``channels_last`` strides, so the rest of PyTorch (and the ATen
+fall-backs used for the few ops that have no hand-written kernel yet) sees
+ordinary tensors, while the kernels receive the underlying [N,H,W,C] buffer.
+
+Kernel inventory (SURVEY §2.10 ids):
+  G1  conv2d_nhwc          tcgen05 implicit GEMM (TMA 4-D boxes -> smem -> UMMA.tf32 -> TMEM), BN stats in epilogue
+  G2/3 bn_elu_fwd/bwd      BatchNorm(train) + residual + ELU fused, two-pass backward
+  G4  avgpool / pool_linear
+  G5  linear_tf32          tcgen05 GEMM with bias+ELU epilogue
+  G9  cross_entropy        fused log-softmax/NLL fwd, softmax-minus-onehot bwd
+  G10 vae_loss             single fused reduction fwd, elementwise bwd
+  G14-16 flat ops          adam_prox, penalty, L-BFGS algebra (see flatops.py)
+  G22 normalize_u8         uint8 NHWC -> normalised float, layout change fused
+
+On a CUDA device a missing extension is an error, never a silent fall-back.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _ext
+
+_EXT = None
+TF32_LINEAR = os.environ.get("FEDB200_TF32_LINEAR", "0") == "1"
+
+
+def ext():
+    global _EXT
+    if _EXT is None:
+        _EXT = _ext.load("fedb200_cuda", required=True)
+    return _EXT
+
+
+def launch_count() -> int:
+    return int(ext().launch_count())
+
+
+# ----------------------------------------------------------------------------
+# flat-vector ops
+# ----------------------------------------------------------------------------
+_STEP_TENSORS = {}
+
+
+def _step_tensor(key, device) -> torch.Tensor:
+    t = _STEP_TENSORS.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=device)
+        _STEP_TENSORS[key] = t
+    return t
+
+
+def adam_prox_step(x, g, m, v, step, lr, beta1, beta2, eps, z=None, y=None, rho=0.0, lambda1=0.0, lambda2=0.0) -> None:
+    """``step`` is either a CUDA int32 tensor holding the (already incremented) step count
+    (graph-capturable) or a Python int (copied into a per-buffer device counter)."""
+    if not torch.is_tensor(step):
+        t = _step_tensor(m.data_ptr(), x.device)
+        t.fill_(int(step))
+        step = t
+    ext().adam_prox(x, g, m, v, step, lr, beta1, beta2, eps, z, y, rho, lambda1, lambda2)
+
+
+def bump_step(step: torch.Tensor) -> None:
+    ext().bump_step(step)
+
+
+def l1_l2(g: torch.Tensor) -> Tuple[float, float]:
+    a, b = ext().l1_l2(g).tolist()
+    return float(a), float(b) ** 0.5
+
+
+def make_pair(g, g_prev, d, t: float, trust: float):
+    y, s, sc = ext().make_pair(g, g_prev, d, t, trust)
+    ys, ss, yy = sc.tolist()
+    return y, s, float(ys), float(ss) ** 0.5, float(yy)
+
+
+def welford_update(g, mean, m2, n: int) -> float:
+    return float(ext().welford(g, mean, m2, int(n)))
+
+
+def penalty_value(x, z=None, y=None, rho=0.0, lambda1=0.0, lambda2=0.0) -> torch.Tensor:
+    return ext().penalty_value(x, z, y, rho, lambda1, lambda2).reshape(())
+
+
+def penalty_grad_(g, x, z=None, y=None, rho=0.0, lambda1=0.0, lambda2=0.0) -> None:
+    ext().penalty_grad(g, x, z, y, rho, lambda1, lambda2)
+
+
+def multi_dot(pairs) -> torch.Tensor:
+    out = []
+    for i in range(0, len(pairs), 8):
+        chunk = pairs[i:i + 8]
+        out.append(ext().multi_dot([a.contiguous() for a, _ in chunk], [b.contiguous() for _, b in chunk]))
+    return torch.cat(out)
+
+
+def lbfgs_two_loop(Y, S, order: Sequence[int], g, H_diag: float) -> torch.Tensor:
+    o = torch.tensor(list(order), dtype=torch.int32, device=g.device)
+    return ext().lbfgs_two_loop(Y, S, o, g, float(H_diag))
+
+
+# ----------------------------------------------------------------------------
+# input pipeline
+# ----------------------------------------------------------------------------
+def normalize_u8(u8_nhwc: torch.Tensor, mean, std, channels_last: bool) -> torch.Tensor:
+    u8 = u8_nhwc.contiguous()
+    if channels_last:
+        out = ext().normalize_u8(u8, list(mean), list(std), 3, False)   # [N,H,W,3]
+        return out.permute(0, 3, 1, 2)
+    return ext().normalize_u8(u8, list(mean), list(std), 3, True)
+
+
+# ----------------------------------------------------------------------------
+# conv + BN + ELU group
+# ----------------------------------------------------------------------------
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[N,H,W,C] contiguous view of a logical NCHW tensor (copying only if it is not channels_last)."""
+    p = x.permute(0, 2, 3, 1)
+    return p if p.is_contiguous() else p.contiguous()
+
+
+def _krsc(w: torch.Tensor) -> torch.Tensor:
+    p = w.permute(0, 2, 3, 1)
+    return p if p.is_contiguous() else p.contiguous()
+
+
+def conv_bn_act_supported(x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d) -> bool:
+    if not (isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d)):
+        return False
+    if conv.bias is not None or conv.groups != 1 or conv.padding_mode != "zeros":
+        return False
+    if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.dilation != (1, 1):
+        return False
+    if x.dtype != torch.float32 or x.dim() != 4 or not bn.training or not bn.track_running_stats or bn.momentum is None:
+        return False
+    kh, kw = conv.kernel_size
+    s, p = conv.stride[0], conv.padding[0]
+    H, W = x.shape[2], x.shape[3]
+    Ho, Wo = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
+    cin = x.shape[1] if x.shape[1] % 4 == 0 else (4 if x.shape[1] == 3 else -1)
+    if cin < 0 or conv.out_channels % 4 != 0:
+        return False
+    return bool(ext().conv_supported(Ho, Wo, cin, s))
+
+
+class _ConvBnAct(torch.autograd.Function):
+    """``act(BN_train(conv(x)) + residual)`` with NHWC kernels; see module docstring."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, running_mean, running_var, stride, pad, eps, momentum, act):
+        e = ext()
+        xn = _nhwc(x)
+        wk = _krsc(weight)
+        if xn.shape[3] == 3:  # stem: pad 3 -> 4 channels so that the pixel pitch is 16 B (TMA requirement)
+            xn = F.pad(xn, (0, 1))
+            wk = F.pad(wk, (0, 1))
+        Co = weight.shape[0]
+        stats = torch.zeros(2 * Co, dtype=torch.float32, device=x.device)
+        y = e.conv2d_nhwc(xn, wk, stats, stride, pad, 1)
+        res = _nhwc(residual) if residual is not None else None
+        out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, res, running_mean, running_var, eps, momentum, act)
+        ctx.save_for_backward(xn, wk, y, out, mean, invstd, gamma)
+        ctx.cfg = (stride, pad, act, residual is not None, tuple(weight.shape), x.shape[1])
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        e = ext()
+        xn, wk, y, out, mean, invstd, gamma = ctx.saved_tensors
+        stride, pad, act, has_res, wshape, cin_logical = ctx.cfg
+        need_x, need_w, need_g, need_b, need_r = ctx.needs_input_grad[:5]
+        dn = _nhwc(dout)
+        dgamma = torch.zeros_like(gamma) if need_g else None
+        dbeta = torch.zeros_like(gamma) if need_b else None
+        dy, dres = e.bn_elu_bwd(dn, out, y, mean, invstd, gamma, dgamma, dbeta, bool(has_res and need_r), act)
+        dx = dw = None
+        kh, kw = wshape[2], wshape[3]
+        if need_x:
+            Ci = xn.shape[3]
+            if stride == 1 and e.conv_supported(xn.shape[1], xn.shape[2], wshape[0], 1) and Ci % 4 == 0:
+                # data gradient of a stride-1 conv = conv of dy with the 180-degree rotated, transposed filter
+                dxn = e.conv2d_nhwc(dy, e.weight_flip(wk), None, 1, kh - 1 - pad, 1)
+            else:
+                dxn = torch.ops.aten.convolution_backward(
+                    dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
+                    [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [True, False, False])[0]
+                dxn = _nhwc(dxn)
+            if dxn.shape[3] != cin_logical:
+                dxn = dxn[..., :cin_logical]
+            dx = dxn.permute(0, 3, 1, 2)
+        if need_w:
+            dwk = torch.ops.aten.convolution_backward(
+                dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
+                [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+            dw = dwk[:, :cin_logical] if dwk.shape[1] != cin_logical else dwk
+        dr = dres.permute(0, 3, 1, 2) if (has_res and need_r and dres is not None) else None
+        return dx, dw, dgamma, dbeta, dr, None, None, None, None, None, None, None
+
+
+def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, residual=None, act: bool = True) -> torch.Tensor:
+    return _ConvBnAct.apply(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var,
+                            conv.stride[0], conv.padding[0], bn.eps, bn.momentum, bool(act))
+
+
+# ----------------------------------------------------------------------------
+# pooling + classifier head
+# ----------------------------------------------------------------------------
+def pool_linear_supported(x, linear, window) -> bool:
+    return x.dim() == 4 and x.shape[2] == window and x.shape[3] == window and x.dtype == torch.float32
+
+
+class _AvgPoolNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xn = _nhwc(x)
+        ctx.hw = (xn.shape[1], xn.shape[2])
+        return ext().avgpool_nhwc(xn)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = ext().avgpool_nhwc_bwd(dout.contiguous(), ctx.hw[0], ctx.hw[1])
+        return dx.permute(0, 3, 1, 2)
+
+
+def pool_linear(x, linear: nn.Linear, window: int) -> torch.Tensor:
+    pooled = _AvgPoolNHWC.apply(x)                     # global average over the window x window map
+    return F.linear(pooled, linear.weight, linear.bias)  # 128x512x10: true fp32, as in the reference
+
+
+# ----------------------------------------------------------------------------
+# dense layers on tensor cores (opt-in: the reference runs nn.Linear in true fp32)
+# ----------------------------------------------------------------------------
+def linear_act_supported(x, linear) -> bool:
+    return (TF32_LINEAR and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0
+            and x.is_contiguous() and linear.weight.is_contiguous())
+
+
+class _LinearAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        out = ext().linear_tf32(x, w, b, act)
+        ctx.save_for_backward(x, w, out)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, out = ctx.saved_tensors
+        if ctx.act:
+            dout = dout * torch.where(out > 0, torch.ones_like(out), out + 1)
+        dx = dout @ w if ctx.needs_input_grad[0] else None
+        dw = dout.t() @ x if ctx.needs_input_grad[1] else None
+        db = dout.sum(0) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def linear_act(x, linear: nn.Linear, act: bool) -> torch.Tensor:
+    return _LinearAct.apply(x, linear.weight, linear.bias, bool(act))
+
+
+def linear_tf32(x, w, b=None, act=False) -> torch.Tensor:
+    return ext().linear_tf32(x.contiguous(), w.contiguous(), b, act)
+
+
+def conv2d_nhwc(x_nhwc, w_krsc, stats=None, stride=1, pad=1) -> torch.Tensor:
+    return ext().conv2d_nhwc(x_nhwc, w_krsc, stats, stride, pad, 1)
+
+
+# ----------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------
+def cross_entropy_supported(logits) -> bool:
+    return logits.dim() == 2 and logits.dtype == torch.float32
+
+
+class _CrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, probs = ext().cross_entropy_fwd(logits.contiguous(), labels)
+        ctx.save_for_backward(probs, labels)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        probs, labels = ctx.saved_tensors
+        return ext().cross_entropy_bwd(probs, labels, gout.reshape(1).float()), None
+
+
+def cross_entropy(logits, labels) -> torch.Tensor:
+    return _CrossEntropy.apply(logits, labels)
+
+
+class _VAELoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, recon, x, mu, logvar):
+        r, xx, m, lv = recon.contiguous(), x.contiguous(), mu.contiguous(), logvar.contiguous()
+        ctx.save_for_backward(r, xx, m, lv)
+        return ext().vae_loss_fwd(r, xx, m, lv)
+
+    @staticmethod
+    def backward(ctx, gout):
+        r, xx, m, lv = ctx.saved_tensors
+        dr, dm, dl = ext().vae_loss_bwd(r, xx, m, lv, gout.reshape(1).float())
+        return dr, None, dm, dl
+
+
+def vae_loss(recon, x, mu, logvar) -> torch.Tensor:
+    return _VAELoss.apply(recon, x, mu, logvar)
+
+
+def info_nce_supported(z) -> bool:
+    return False  # vectorised ATen expression for now (one GEMM + softmax); fused kernel is future work

@@ -169,6 +169,16 @@ def penalty_grad(x, g, z=None, y=None, rho: float = 0.0, lambda1: float = 0.0, l
     return gt
 
 
+def add_penalty_grad_(g, x, z=None, y=None, rho: float = 0.0, lambda1: float = 0.0, lambda2: float = 0.0) -> None:
+    """In place ``g += y + rho (x - z) + lambda1 sign(x) + 2 lambda2 x`` (one kernel on CUDA)."""
+    if _cuda(g):
+        from . import cuda_ops
+
+        cuda_ops.penalty_grad_(g, x, z, y, rho, lambda1, lambda2)
+        return
+    g.copy_(penalty_grad(x, g, z, y, rho, lambda1, lambda2))
+
+
 def penalty_value(x, z=None, y=None, rho: float = 0.0, lambda1: float = 0.0, lambda2: float = 0.0) -> torch.Tensor:
     """``y.(x-z) + rho/2 ||x-z||^2 + lambda1 ||x||_1 + lambda2 ||x||_2^2`` as a 0-dim tensor."""
     if _cuda(x):

@@ -39,6 +39,8 @@ class BlockAdam(Optimizer):
         self.m = torch.zeros(b - a, dtype=torch.float32, device=arena.data.device)
         self.v = torch.zeros_like(self.m)
         self.t = 0
+        # device-resident step counter: lets the update be replayed from a CUDA graph (no host-side scalars)
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=arena.data.device) if arena.data.is_cuda else None
         # penalty configuration (set by the aggregation strategy for the current block visit)
         self.z: Optional[torch.Tensor] = None
         self.y: Optional[torch.Tensor] = None
@@ -63,6 +65,8 @@ class BlockAdam(Optimizer):
         self.m.zero_()
         self.v.zero_()
         self.t = 0
+        if self.t_dev is not None:
+            self.t_dev.zero_()
         if lr is not None:
             self.param_groups[0]["lr"] = lr
 
@@ -74,7 +78,13 @@ class BlockAdam(Optimizer):
         """The update alone (gradients already in the arena); CUDA-graph friendly: no host reads."""
         self.t += 1
         grp = self.param_groups[0]
-        flatops.adam_prox_step(self.x, self.g, self.m, self.v, self.t, grp["lr"], grp["betas"][0], grp["betas"][1],
+        step = self.t
+        if self.t_dev is not None and flatops._cuda(self.x):
+            from ..ops import cuda_ops
+
+            cuda_ops.bump_step(self.t_dev)
+            step = self.t_dev
+        flatops.adam_prox_step(self.x, self.g, self.m, self.v, step, grp["lr"], grp["betas"][0], grp["betas"][1],
                                grp["eps"], self.z, self.y, self.rho, self.lambda1, self.lambda2)
 
     def step(self, closure: Optional[Callable] = None):

@@ -45,6 +45,11 @@ class TorchCollective:
     def register_arena(self, arena) -> None:
         return None
 
+    def zeros_like_block(self, x: torch.Tensor, tag: str) -> torch.Tensor:
+        """Zeroed companion vector of block slice ``x`` (ADMM duals).  The fused backend returns a slice of a
+        symmetric arena so that peers can read it."""
+        return torch.zeros_like(x)
+
     # -- primitives -------------------------------------------------------
     def _allreduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.topo.is_distributed:
