@@ -74,7 +74,7 @@ def _override(src: str, consts: Dict[str, object]) -> str:
 
 
 def run_reference_script(script: str, consts: Dict[str, object], steps: Optional[int] = None, warmup: int = 0,
-                         workdir: Optional[str] = None) -> Dict:
+                         workdir: Optional[str] = None, on_timed_start=None) -> Dict:
     """Execute ``baseline/_ref/src/<script>``; if ``steps`` is given stop after ``warmup+steps`` Adam steps."""
     path = os.path.join(REF_SRC, script)
     if not os.path.exists(path):
@@ -91,6 +91,8 @@ def run_reference_script(script: str, consts: Dict[str, object], steps: Optional
             if cuda:
                 torch.cuda.synchronize()
                 state["ev0"] = torch.cuda.Event(enable_timing=True)
+                if on_timed_start is not None:
+                    on_timed_start()
                 state["ev0"].record()
             state["t0"] = time.perf_counter()
         out = orig_step(self, closure)
@@ -144,8 +146,8 @@ def run_reference_bench(gpus: int, steps: int, warmup: int) -> Dict:
     from bench import ClockSampler  # same clock sampling as the product arm
 
     sampler = ClockSampler(0)
-    sampler.start()
-    res = run_reference_script("federated_multi.py", consts, steps=steps * gpus, warmup=warmup * gpus, workdir="/tmp/fedref_run")
+    res = run_reference_script("federated_multi.py", consts, steps=steps * gpus, warmup=warmup * gpus, workdir="/tmp/fedref_run",
+                               on_timed_start=sampler.start)   # clocks sampled during the timed region only
     clocks = sampler.stop()
     ms = max(res.get("device_ms", 0.0), res.get("wall_ms", 0.0))
     images = 128 * gpus * steps

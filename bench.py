@@ -104,7 +104,7 @@ def run_ours(args) -> dict:
         cfg = federated_multi.Config(
             K=N, use_resnet=True, Nloop=1000, Nadmm=3, Nepoch=1, check_results=False, save_model=False, be_verbose=False,
             biased_input=True, data_on_device=data_on_device, graphs=not args.no_graphs, fast=not args.no_fast,
-            collective="auto", diagnostics=args.diagnostics, max_minibatches=STEPS_PER_ROUND, seed=69)
+            collective=args.collective, diagnostics=args.diagnostics, max_minibatches=STEPS_PER_ROUND, seed=69)
         topo, coll = common.setup_runtime(cfg)
         task = common.ClassifierTask(cfg, topo, cfg.lambda1, cfg.lambda2)
         strat = FedAvg(coll, topo) if args.algo == "fedavg" else ADMM(coll, topo, len(task.blocks), 0.1)
@@ -154,7 +154,7 @@ def run_ours(args) -> dict:
     out = {
         "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": N, "steps": K, "warmup": W,
         "ms_per_step": dev_run["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if not args.no_fast else "fp32(tf32 conv)", "data": "synthetic", "impl": "ours",
+        "dtype": "tf32" if not args.no_fast else "fp32(tf32 conv)", "data": "synthetic", "impl": args.impl,
         "config": {"model": "ResNet18", "algo": args.algo, "global_batch": 128 * N, "per_gpu_batch": 128, "K": N,
                    "parallelism": "fed%d (one replica per GPU, block FedAvg over NVLink)" % N,
                    "steps_per_round": STEPS_PER_ROUND, "diagnostics_forward": args.diagnostics, "cuda_graphs": not args.no_graphs,
@@ -177,13 +177,17 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"],
+                    help="ours | reference (unmodified reference via shim) | nccl (BASELINE 'ref-nccl': ATen model + NCCL all-reduce)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "fused", "torch"])
     ap.add_argument("--algo", default="fedavg", choices=["fedavg", "admm"])
     ap.add_argument("--diagnostics", default="post", choices=["post", "pre"])
     ap.add_argument("--no-graphs", dest="no_graphs", action="store_true")
     ap.add_argument("--no-fast", dest="no_fast", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.impl == "nccl":   # the "baseline, not the product": stock ATen ops, eager, NCCL all-reduce on the flat block
+        args.no_fast, args.no_graphs, args.collective = True, True, "torch"
 
     if args.impl == "reference":
         from baseline.ref_shim import run_reference_bench
