@@ -1,8 +1,9 @@
-// Host side of the tcgen05 implicit-GEMM kernel: TMA tensor-map construction and launch.
+// Host side of the tcgen05 implicit-GEMM kernel: TMA tensor-map construction, tile/cluster selection, launch.
 // (Kernel: igemm_tcgen05.cuh.)  Torch-free translation unit: raw pointers + cudaStream_t.
 #include "fedb200.h"
 #include "igemm_tcgen05.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -66,39 +67,74 @@ static CUtensorMap make_tmap_nhwc(const float* ptr, uint64_t N, uint64_t H, uint
   return m;
 }
 
-template <int BN, int ST>
+template <int BN, int ST, int CL>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
   using S = IgemmSmem<BN, ST>;
+  auto kernel = igemm_tf32_kernel<BN, ST, CL>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tf32_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((p.M + IG_BLOCK_M - 1) / IG_BLOCK_M, (p.N + BN - 1) / BN);
-  igemm_tf32_kernel<BN, ST><<<grid, IG_THREADS, S::TOTAL, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  const int mt = (p.M + IG_BLOCK_M - 1) / IG_BLOCK_M;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(((mt + CL - 1) / CL) * CL, (p.N + BN - 1) / BN);   // padded M tiles only feed the multicast
+  cfg.blockDim = dim3(IG_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: igemm launch: ") + cudaGetErrorString(e));
   count_launch();
 }
 
-static void dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
+template <int BN, int ST>
+static void dispatch_cl(int cl, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
+  if (cl >= 4) launch<BN, ST, 4>(ta, tb, p, s);
+  else if (cl == 2) launch<BN, ST, 2>(ta, tb, p, s);
+  else launch<BN, ST, 1>(ta, tb, p, s);
+}
+
+static void dispatch(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
   switch (bn) {
-    case 32: launch<32, 8>(ta, tb, p, s); break;
-    case 64: launch<64, 6>(ta, tb, p, s); break;
-    case 128: launch<128, 5>(ta, tb, p, s); break;
-    default: launch<256, 4>(ta, tb, p, s); break;
+    case 32: dispatch_cl<32, 8>(cl, ta, tb, p, s); break;
+    case 64: dispatch_cl<64, 6>(cl, ta, tb, p, s); break;
+    case 128: dispatch_cl<128, 5>(cl, ta, tb, p, s); break;
+    default: dispatch_cl<256, 4>(cl, ta, tb, p, s); break;
   }
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+// The kernel is L2->SM bandwidth bound: bytes moved = A_bytes * taps * (N / BLOCK_N) + W_bytes * (M tiles / CL).
+// So: the widest N tile that N allows (fewer passes over the activations) and the largest cluster (fewer passes
+// over the weights).  FEDB200_BLOCK_N / FEDB200_CLUSTER override for experiments.
 int pick_block_n(int M, int N) {
+  const int forced = env_int("FEDB200_BLOCK_N", 0);
+  if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
+  (void)M;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 256;
+}
+static int pick_cluster(int M) {
+  const int forced = env_int("FEDB200_CLUSTER", -1);
+  if (forced == 1 || forced == 2 || forced == 4) return forced;
   const int mt = (M + IG_BLOCK_M - 1) / IG_BLOCK_M;
-  // prefer the widest tile that still yields at least one full wave of 148 CTAs
-  if (N >= 256 && mt * ((N + 255) / 256) >= 148) return 256;
-  if (mt * ((N + 127) / 128) >= 148 || N <= 128) return 128;
-  return 64;
+  if (mt >= 8) return 4;
+  if (mt >= 2) return 2;
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -107,15 +143,16 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
   if ((ldx & 3) || (ldw & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
     throw std::runtime_error("fedb200: linear_tf32 needs 16-byte aligned rows");
   const int bn = pick_block_n(M, N);
+  const int cl = pick_cluster(M);
   CUtensorMap ta = make_tmap_2d(x, M, K, ldx, IG_BLOCK_M);
-  CUtensorMap tb = make_tmap_2d(w, N, K, ldw, bn);
+  CUtensorMap tb = make_tmap_2d(w, N, K, ldw, bn / cl);
   IgemmParams p{};
   p.M = M; p.N = N;
   p.cblocks = (K + IG_BLOCK_K - 1) / IG_BLOCK_K;
   p.num_k_blocks = p.cblocks;
   p.taps_w = 1; p.b_cols_per_tap = 0; p.is_conv = 0;
   p.out = out; p.ldo = ldo; p.bias = bias; p.act = act; p.stats = nullptr;
-  dispatch(bn, ta, tb, p, stream);
+  dispatch(bn, cl, ta, tb, p, stream);
 }
 
 bool conv_geometry_supported(int H_out, int W_out, int C_in, int stride) {
@@ -137,8 +174,9 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   const int boxN = rows <= H_out ? 1 : rows / H_out;
   const int M = NB * H_out * W_out;
   const int bn = pick_block_n(M, C_out);
+  const int cl = pick_cluster(M);
   CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
-  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn);
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn / cl);
   IgemmParams p{};
   p.M = M; p.N = C_out;
   p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
@@ -147,7 +185,7 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   p.HW_out = H_out * W_out; p.W_out = W_out;
   p.stride = stride; p.pad = pad; p.dil = dil;
   p.out = y; p.ldo = C_out; p.bias = nullptr; p.act = 0; p.stats = stats;
-  dispatch(bn, ta, tb, p, stream);
+  dispatch(bn, cl, ta, tb, p, stream);
 }
 
 }  // namespace fedb200

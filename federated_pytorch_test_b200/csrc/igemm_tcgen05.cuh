@@ -10,6 +10,11 @@
 //   * per-channel sum / sum-of-squares of the tile (BatchNorm batch statistics, reduced across the CTA in shared
 //     memory, one atomicAdd per channel per CTA) — SURVEY G1/G2.
 //
+// The kernel is L2->SM bandwidth bound (measured: ~6.5 TB/s, profiles/r1_run2_*), so operand re-reads are what
+// matters.  CL > 1 launches thread-block clusters of CL CTAs that own CL consecutive M tiles of the same N tile:
+// each CTA fetches 1/CL of the weight tile and TMA-multicasts it into the shared memory of all CL CTAs
+// (weight traffic / CL); the smem-slot release is a tcgen05.commit multicast to every CTA of the cluster.
+//
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), one tmem_full mbarrier (MMA -> epilogue).
 #pragma once
@@ -49,13 +54,17 @@ struct IgemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + PART_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CL>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
   using S = IgemmSmem<BLOCK_N, STAGES>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N must be a multiple of 32 in [32,256]");
+  static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size 1, 2 or 4");
+  static_assert((BLOCK_N / CL) % 8 == 0, "each CTA's slice of the weight tile must be whole swizzle atoms");
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 for 32/64/128/256
+  constexpr int B_SLICE_ROWS = BLOCK_N / CL;
+  constexpr uint16_t CL_MASK = uint16_t((1u << CL) - 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -71,13 +80,14 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * IG_BLOCK_M;
   const int n0 = blockIdx.y * BLOCK_N;
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);        // every CTA of the cluster releases the slot (it holds multicast data)
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -87,7 +97,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -115,7 +125,14 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         } else {
           tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * IG_BLOCK_K, m0);
         }
-        tma_load_2d(b_dst, &tmap_b, &full_bar[s], tap * p.b_cols_per_tap + cb * IG_BLOCK_K, n0);
+        const int b_col = tap * p.b_cols_per_tap + cb * IG_BLOCK_K;
+        if (CL == 1) {
+          tma_load_2d(b_dst, &tmap_b, &full_bar[s], b_col, n0);
+        } else {
+          // my 1/CL slice of the weight tile, written into the same slot of every CTA in the cluster
+          tma_load_2d_multicast(b_dst + cta_rank * (B_SLICE_ROWS * IG_BLOCK_K * 4), &tmap_b, &full_bar[s], b_col,
+                                n0 + int(cta_rank) * B_SLICE_ROWS, CL_MASK);
+        }
       }
     }
   } else if (warp == 1) {
@@ -136,7 +153,8 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // advance along K inside the 128-B swizzle atom: +32 B per step (encoded >>4 => +2)
           umma_tf32(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);                 // frees the smem slot when these MMAs retire
+        // free the smem slot (in every CTA of the cluster) when these MMAs retire
+        if (CL == 1) umma_commit(&empty_bar[s]); else umma_commit_multicast(&empty_bar[s], CL_MASK);
         if (kb == p.num_k_blocks - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
@@ -210,7 +228,8 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     tc_fence_before();
   }
-  __syncthreads();
+  // no CTA may leave while a peer can still multicast into its shared memory / arrive on its barriers
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
