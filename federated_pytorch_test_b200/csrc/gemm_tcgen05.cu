@@ -2,6 +2,9 @@
 // (Kernel: igemm_tcgen05.cuh.)  Torch-free translation unit: raw pointers + cudaStream_t.
 #include "fedb200.h"
 #include "igemm_tcgen05.cuh"
+#include "conv_halo_tcgen05.cuh"
+#include "igemm2_tcgen05.cuh"
+#include "conv_ws_tcgen05.cuh"
 
 #include <cstdlib>
 #include <mutex>
@@ -32,6 +35,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// TFLOAT32 makes the TMA unit round fp32 -> tf32 (nearest) on the way into shared memory; FLOAT32 copies the bits and
+// the tensor core truncates the low 13 mantissa bits.  FEDB200_TMAP_F32=1 selects the latter (experiments).
+static CUtensorMapDataType tmap_dtype() {
+  const char* v = std::getenv("FEDB200_TMAP_F32");
+  return (v && std::atoi(v) == 1) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+}
+
 static void check_cu(CUresult r, const char* what) {
   if (r != CUDA_SUCCESS) throw std::runtime_error(std::string("fedb200: ") + what + " failed with CUresult " + std::to_string(int(r)));
 }
@@ -44,7 +54,7 @@ static CUtensorMap make_tmap_2d(const float* ptr, uint64_t rows, uint64_t cols, 
   cuuint64_t strides[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {uint32_t(IG_BLOCK_K), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  check_cu(encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  check_cu(encode_fn()(&m, tmap_dtype(),2, const_cast<float*>(ptr), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
            "cuTensorMapEncodeTiled(2d)");
@@ -60,7 +70,7 @@ static CUtensorMap make_tmap_nhwc(const float* ptr, uint64_t N, uint64_t H, uint
   cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
   cuuint32_t box[4] = {uint32_t(IG_BLOCK_K), boxW * stride, boxH * stride, boxN};
   cuuint32_t estr[4] = {1, stride, stride, 1};
-  check_cu(encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+  check_cu(encode_fn()(&m, tmap_dtype(),4, const_cast<float*>(ptr), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
            "cuTensorMapEncodeTiled(nhwc)");
@@ -79,7 +89,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmPara
   }
   const int mt = (p.M + IG_BLOCK_M - 1) / IG_BLOCK_M;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(((mt + CL - 1) / CL) * CL, (p.N + BN - 1) / BN);   // padded M tiles only feed the multicast
+  cfg.gridDim = dim3(((mt + CL - 1) / CL) * CL, (p.N + BN - 1) / BN, p.k_splits);   // padded M tiles only feed the multicast
   cfg.blockDim = dim3(IG_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
@@ -116,6 +126,46 @@ static int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
+// ---- CTA-pair kernel (igemm2_tcgen05.cuh): 256 x BN tile per pair of SMs ----
+template <int BN, int ST>
+static void launch2(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
+  using S = Igemm2Smem<BN, ST>;
+  auto kernel = igemm2_tf32_kernel<BN, ST>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(2cta): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const int mt = (p.M + IG_BLOCK_M - 1) / IG_BLOCK_M;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(((mt + 1) / 2) * 2, (p.N + BN - 1) / BN, 1);
+  cfg.blockDim = dim3(IG_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, p);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: igemm2 launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+static void dispatch2(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
+  switch (bn) {
+    case 64: launch2<64, 8>(ta, tb, p, s); break;
+    case 128: launch2<128, 7>(ta, tb, p, s); break;
+    default: launch2<256, 6>(ta, tb, p, s); break;
+  }
+}
+static bool use_pair_kernel(int M, int bn) {
+  // opt-in (FEDB200_2CTA=1): numerically verified, but no faster than the single-CTA kernel on these shapes (measured)
+  return env_int("FEDB200_2CTA", 0) != 0 && bn >= 64 && M > IG_BLOCK_M;
+}
+
 // The kernel is L2->SM bandwidth bound: bytes moved = A_bytes * taps * (N / BLOCK_N) + W_bytes * (M tiles / CL).
 // So: the widest N tile that N allows (fewer passes over the activations) and the largest cluster (fewer passes
 // over the weights).  FEDB200_BLOCK_N / FEDB200_CLUSTER override for experiments.
@@ -129,12 +179,12 @@ int pick_block_n(int M, int N) {
   return 256;
 }
 static int pick_cluster(int M) {
-  const int forced = env_int("FEDB200_CLUSTER", -1);
-  if (forced == 1 || forced == 2 || forced == 4) return forced;
-  const int mt = (M + IG_BLOCK_M - 1) / IG_BLOCK_M;
-  if (mt >= 8) return 4;
-  if (mt >= 2) return 2;
-  return 1;
+  // Measured (profiles/r1_run5_*, r1_run6_*): multicasting the weight tile across 2/4 CTAs does not change the
+  // kernel time on B200 — L2 already merges the near-simultaneous requests of neighbouring CTAs.  Kept as an
+  // opt-in experiment (FEDB200_CLUSTER=2|4).
+  const int forced = env_int("FEDB200_CLUSTER", 1);
+  (void)M;
+  return (forced == 2 || forced == 4) ? forced : 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -143,7 +193,8 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
   if ((ldx & 3) || (ldw & 3) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15))
     throw std::runtime_error("fedb200: linear_tf32 needs 16-byte aligned rows");
   const int bn = pick_block_n(M, N);
-  const int cl = pick_cluster(M);
+  const bool pair = use_pair_kernel(M, bn);
+  const int cl = pair ? 2 : pick_cluster(M);
   CUtensorMap ta = make_tmap_2d(x, M, K, ldx, IG_BLOCK_M);
   CUtensorMap tb = make_tmap_2d(w, N, K, ldw, bn / cl);
   IgemmParams p{};
@@ -152,7 +203,8 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
   p.num_k_blocks = p.cblocks;
   p.taps_w = 1; p.b_cols_per_tap = 0; p.is_conv = 0;
   p.out = out; p.ldo = ldo; p.bias = bias; p.act = act; p.stats = nullptr;
-  dispatch(bn, cl, ta, tb, p, stream);
+  p.k_splits = 1; p.kb_per_split = p.num_k_blocks;
+  if (pair) dispatch2(bn, ta, tb, p, stream); else dispatch(bn, cl, ta, tb, p, stream);
 }
 
 bool conv_geometry_supported(int H_out, int W_out, int C_in, int stride) {
@@ -165,8 +217,142 @@ bool conv_geometry_supported(int H_out, int W_out, int C_in, int stride) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 / s1 / p1 through the shared-memory halo kernel (conv_halo_tcgen05.cuh)
+// ------------------------------------------------------------------------------------------------
+template <int BN, int SLOT, int CL>
+static void launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, cudaStream_t stream) {
+  using S = HaloSmem<BN, SLOT>;
+  auto kernel = conv3x3_halo_kernel<BN, SLOT, CL>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(halo): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = p.NB * p.tiles_per_img;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(((tiles + CL - 1) / CL) * CL, p.C_out / BN);
+  cfg.blockDim = dim3(IG_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, p);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: halo conv launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+
+static bool halo_applicable(int H, int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil) {
+  const int mode = env_int("FEDB200_HALO", 1);   // 0 off, 1 = 32-wide maps only (where it wins), 2 = also 16-wide
+  if (mode == 0) return false;
+  if (kh != 3 || kw != 3 || stride != 1 || pad != 1 || dil != 1) return false;
+  if (!(W == 32 || (W == 16 && mode >= 2)) || H < 4) return false;   // 16x16: slower than the generic kernel (measured)
+  if ((C_in & 3) || (C_out % 64) != 0) return false;
+  return true;
+}
+
+static void conv3x3_halo(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in,
+                         int C_out, cudaStream_t stream) {
+  HaloParams p{};
+  p.NB = NB; p.H = H; p.W = W; p.Wp = W + 2;
+  p.R = (p.Wp - 1 + 127 + 2 * p.Wp + 2) / p.Wp + 1;
+  p.tiles_per_img = (H * p.Wp + IG_BLOCK_M - 1) / IG_BLOCK_M;
+  p.C_in = C_in; p.C_out = C_out; p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
+  p.a_box_bytes = 128 * p.Wp * p.R;
+  // measured: the UMMA unit derives the swizzle phase from the absolute smem address, so a row-offset start needs
+  // base_offset = 0 (encoding (addr>>7)&7 double-counts and scrambles the tile) — profiles/r1_run6_conv_variants.log
+  p.use_base_offset = env_int("FEDB200_HALO_BO", 0);
+  p.out = y; p.stats = stats;
+  const int cl = 1;   // weight multicast buys nothing (L2 already de-duplicates cluster-sized bursts; measured) -> keep it simple
+  // activation [C, W, H, N]: box = 32 channels x Wp columns x R rows of one image, no traversal stride
+  CUtensorMap ta;
+  {
+    cuuint64_t dims[4] = {cuuint64_t(C_in), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
+    cuuint64_t strides[3] = {cuuint64_t(C_in) * 4, cuuint64_t(W) * C_in * 4, cuuint64_t(H) * W * C_in * 4};
+    cuuint32_t box[4] = {uint32_t(IG_BLOCK_K), uint32_t(p.Wp), uint32_t(p.R), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    check_cu(encode_fn()(&ta, tmap_dtype(),4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+             "cuTensorMapEncodeTiled(halo)");
+  }
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(9) * C_in, uint64_t(9) * C_in, 64 / cl);
+  if (W == 32) {
+    if (p.a_box_bytes > 30720) throw std::runtime_error("fedb200: halo box does not fit its slot");
+    if (cl == 4) launch_halo<64, 30720, 4>(ta, tb, p, stream); else launch_halo<64, 30720, 1>(ta, tb, p, stream);
+  } else {
+    if (p.a_box_bytes > 25600) throw std::runtime_error("fedb200: halo box does not fit its slot");
+    if (cl == 4) launch_halo<64, 25600, 4>(ta, tb, p, stream); else launch_halo<64, 25600, 1>(ta, tb, p, stream);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-stationary persistent kernel (conv_ws_tcgen05.cuh): C_out = 64, C_in <= 64, 32-wide maps
+// ------------------------------------------------------------------------------------------------
+static bool ws_applicable(int H, int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil) {
+  if (env_int("FEDB200_WS", 1) == 0) return false;
+  if (kh != 3 || kw != 3 || stride != 1 || pad != 1 || dil != 1) return false;
+  return W == 32 && H >= 4 && C_out == WS_BN && C_in <= 64 && (C_in & 3) == 0;
+}
+
+static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
+                       cudaStream_t stream) {
+  HaloParams p{};
+  p.NB = NB; p.H = H; p.W = W; p.Wp = W + 2;
+  p.R = (p.Wp - 1 + 127 + 2 * p.Wp + 2) / p.Wp + 1;
+  p.tiles_per_img = (H * p.Wp + IG_BLOCK_M - 1) / IG_BLOCK_M;
+  p.C_in = C_in; p.C_out = C_out; p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
+  p.a_box_bytes = 128 * p.Wp * p.R;
+  p.use_base_offset = 0;
+  p.out = y; p.stats = stats;
+  if (p.a_box_bytes > WS_A_SLOT) throw std::runtime_error("fedb200: halo box does not fit its slot (ws)");
+  CUtensorMap ta;
+  {
+    cuuint64_t dims[4] = {cuuint64_t(C_in), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
+    cuuint64_t strides[3] = {cuuint64_t(C_in) * 4, cuuint64_t(W) * C_in * 4, cuuint64_t(H) * W * C_in * 4};
+    cuuint32_t box[4] = {uint32_t(IG_BLOCK_K), uint32_t(p.Wp), uint32_t(p.R), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    check_cu(encode_fn()(&ta, tmap_dtype(), 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+             "cuTensorMapEncodeTiled(ws)");
+  }
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(9) * C_in, uint64_t(9) * C_in, WS_BN);
+  static int sms = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WsSmem::TOTAL);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(ws): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = NB * p.tiles_per_img;
+  const int grid = tiles < sms ? tiles : sms;
+  conv3x3_ws_kernel<<<grid, IG_THREADS, WsSmem::TOTAL, stream>>>(ta, tb, p, tiles);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: ws conv launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+
 void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
                       int kh, int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream) {
+  if (ws_applicable(H, W, C_in, C_out, kh, kw, stride, pad, dil)) {
+    conv3x3_ws(x, w, y, stats, NB, H, W, C_in, C_out, stream);
+    return;
+  }
+  if (halo_applicable(H, W, C_in, C_out, kh, kw, stride, pad, dil)) {
+    conv3x3_halo(x, w, y, stats, NB, H, W, C_in, C_out, stream);
+    return;
+  }
   if (!conv_geometry_supported(H_out, W_out, C_in, stride))
     throw std::runtime_error("fedb200: conv geometry not supported by the tcgen05 path");
   const int rows = 128 / W_out;
@@ -174,7 +360,8 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   const int boxN = rows <= H_out ? 1 : rows / H_out;
   const int M = NB * H_out * W_out;
   const int bn = pick_block_n(M, C_out);
-  const int cl = pick_cluster(M);
+  const bool pair = use_pair_kernel(M, bn);
+  const int cl = pair ? 2 : pick_cluster(M);
   CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
   CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn / cl);
   IgemmParams p{};
@@ -185,7 +372,28 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   p.HW_out = H_out * W_out; p.W_out = W_out;
   p.stride = stride; p.pad = pad; p.dil = dil;
   p.out = y; p.ldo = C_out; p.bias = nullptr; p.act = 0; p.stats = stats;
-  dispatch(bn, cl, ta, tb, p, stream);
+  p.k_splits = 1; p.kb_per_split = p.num_k_blocks;
+  // Split-K: the kernel is bound by what ONE SM can ingest (~40-60 B/cycle, profiles/r1_run8_*), so a grid that
+  // leaves SMs idle (64 CTAs for layer3, 32 for layer4 with 128x256 tiles) wastes most of the chip.  Slice K until
+  // ~one full wave of CTAs exists; partial tiles are reduced with red.global.add.v4 into a zeroed output and the
+  // BatchNorm statistics come from a separate column pass (the outputs of these layers are only 4-8 MB).
+  if (!pair && cl == 1) {
+    const int ctas = ((M + IG_BLOCK_M - 1) / IG_BLOCK_M) * ((C_out + bn - 1) / bn);
+    int splits = env_int("FEDB200_SPLITK", 0);
+    if (splits <= 0) {
+      splits = 1;
+      while (splits < 8 && ctas * splits * 2 <= 160 && p.num_k_blocks / (splits * 2) >= 6) splits *= 2;
+    }
+    if (splits > 1) {
+      p.k_splits = splits;
+      p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+      p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty slices
+      p.stats = nullptr;
+      cudaMemsetAsync(y, 0, size_t(M) * C_out * sizeof(float), stream);
+    }
+  }
+  if (pair) dispatch2(bn, ta, tb, p, stream); else dispatch(bn, cl, ta, tb, p, stream);
+  if (p.k_splits > 1 && stats != nullptr) col_stats(y, stats, M, C_out, stream);
 }
 
 }  // namespace fedb200

@@ -41,6 +41,8 @@ struct IgemmParams {
   const float* bias;     // [N] or nullptr
   int act;               // 1 = ELU
   float* stats;          // [2*N]: sum, sumsq per column (atomicAdd) or nullptr
+  int kb_per_split;      // split-K: CTA z handles k-blocks [z*kb_per_split, ...) and red.adds into a zeroed output
+  int k_splits;          // 1 = plain stores (+ fused stats); > 1 = reduction through L2 atomics, stats done by caller
 };
 
 template <int BLOCK_N, int STAGES>
@@ -81,6 +83,8 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int m0 = blockIdx.x * IG_BLOCK_M;
   const int n0 = blockIdx.y * BLOCK_N;
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int kb_begin = blockIdx.z * p.kb_per_split;                 // split-K slice of this CTA
+  const int kb_count = min(p.kb_per_split, p.num_k_blocks - kb_begin);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -109,9 +113,10 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         img = m0 / p.HW_out;
         h_base = (m0 % p.HW_out) / p.W_out;
       }
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int it = 0; it < kb_count; ++it) {
+        const int kb = kb_begin + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* a_dst = tiles + s * S::STAGE_BYTES;
         uint8_t* b_dst = a_dst + S::A_BYTES;
@@ -138,9 +143,9 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BLOCK_N);
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
+    for (int it = 0; it < kb_count; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (lane == 0) {
@@ -151,11 +156,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
           // advance along K inside the 128-B swizzle atom: +32 B per step (encoded >>4 => +2)
-          umma_tf32(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
         }
         // free the smem slot (in every CTA of the cluster) when these MMAs retire
         if (CL == 1) umma_commit(&empty_bar[s]); else umma_commit_multicast(&empty_bar[s], CL_MASK);
-        if (kb == p.num_k_blocks - 1) umma_commit(tmem_full_bar);
+        if (it == kb_count - 1) umma_commit(tmem_full_bar);
       }
       __syncwarp();
     }
@@ -184,7 +189,17 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (row_ok) {
         float* dst = p.out + size_t(row) * p.ldo + n0 + c0;
-        if (n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+        if (p.k_splits > 1) {
+          // partial sums of this K slice: vector reduction into the (pre-zeroed) output, resolved in L2
+          if (n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);
+          }
+        } else if (n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
         } else {

@@ -152,6 +152,30 @@ def conv_bn_act_supported(x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d) 
     return bool(ext().conv_supported(Ho, Wo, cin, s))
 
 
+_FLIP_CACHE = {}
+
+
+def clear_caches() -> None:
+    """Drop cached derived tensors (call after loading a checkpoint into existing parameters)."""
+    _FLIP_CACHE.clear()
+
+
+def _flipped_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
+    """Rotated/transposed filter for the data gradient.  Frozen layers never change during a block visit (only the
+    active block is optimised or written back by FedAvg), so their flipped copy is computed once and reused; the
+    active block's is recomputed every step."""
+    key = (wk.data_ptr(), tuple(wk.shape))
+    if trainable:
+        _FLIP_CACHE.pop(key, None)
+        return ext().weight_flip(wk)
+    hit = _FLIP_CACHE.get(key)
+    if hit is None:
+        hit = ext().weight_flip(wk)
+        if not torch.cuda.is_current_stream_capturing():   # graph-pool memory must not escape its graph
+            _FLIP_CACHE[key] = hit
+    return hit
+
+
 class _ConvBnAct(torch.autograd.Function):
     """``act(BN_train(conv(x)) + residual)`` with NHWC kernels; see module docstring."""
 
@@ -188,7 +212,7 @@ class _ConvBnAct(torch.autograd.Function):
             Ci = xn.shape[3]
             if stride == 1 and e.conv_supported(xn.shape[1], xn.shape[2], wshape[0], 1) and Ci % 4 == 0:
                 # data gradient of a stride-1 conv = conv of dy with the 180-degree rotated, transposed filter
-                dxn = e.conv2d_nhwc(dy, e.weight_flip(wk), None, 1, kh - 1 - pad, 1)
+                dxn = e.conv2d_nhwc(dy, _flipped_weight(wk, need_w), None, 1, kh - 1 - pad, 1)
             else:
                 dxn = torch.ops.aten.convolution_backward(
                     dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,

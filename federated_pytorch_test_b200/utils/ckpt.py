@@ -37,6 +37,10 @@ def load_into(net: nn.Module, state: Dict[str, torch.Tensor]) -> None:
     with torch.no_grad():
         for k, v in own.items():
             v.copy_(state[k].to(v.device))
+    if any(v.is_cuda for v in own.values()):
+        from ..ops import cuda_ops
+
+        cuda_ops.clear_caches()   # derived tensors (e.g. flipped dgrad filters) of frozen layers are now stale
 
 
 def worker_path(ckpt_dir: str, ck: int, stem: str = "s") -> str:

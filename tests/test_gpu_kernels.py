@@ -381,3 +381,34 @@ def test_host_resident_loader_matches_device_resident():
     for (xa, ya), (xb, yb) in zip(a, b):
         torch.testing.assert_close(xa, xb)
         assert torch.equal(ya, yb)
+
+
+# ------------------------------------------------------------------------------------------ conv kernel variants
+VARIANT_ENVS = [
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1"),                       # generic single-CTA kernel
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="4"),                       # split-K with red.global.add
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_CLUSTER="4"),  # weight-tile TMA multicast
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_2CTA="1"),     # cta_group::2 pairs
+    dict(FEDB200_WS="0", FEDB200_HALO="2"),                                           # halo tile, one box for 9 taps
+    dict(FEDB200_WS="1"),                                                             # weight-stationary persistent
+]
+
+
+@pytest.mark.parametrize("env", VARIANT_ENVS, ids=lambda e: ",".join("%s=%s" % (k[8:], v) for k, v in e.items()))
+@pytest.mark.parametrize("B,H,Ci,Co", [(5, 32, 64, 64), (3, 32, 4, 64), (6, 16, 128, 128), (16, 8, 256, 256)])
+def test_conv_kernel_variants(monkeypatch, env, B, H, Ci, Co):
+    import os
+    for k in ("FEDB200_WS", "FEDB200_HALO", "FEDB200_SPLITK", "FEDB200_CLUSTER", "FEDB200_2CTA", "FEDB200_BLOCK_N"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = torch.Generator(device=DEV).manual_seed(B + H + Ci)
+    x = torch.randn(B, H, H, Ci, device=DEV, generator=g)
+    w = torch.randn(Co, 3, 3, Ci, device=DEV, generator=g) / math.sqrt(9 * Ci)
+    stats = torch.zeros(2 * Co, device=DEV)
+    y = cuda_ops.conv2d_nhwc(x, w, stats, 1, 1)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), None, 1, 1).permute(0, 2, 3, 1).float()
+    assert rel_err(y, ref) < 3e-3
+    flat = ref.reshape(-1, Co)
+    torch.testing.assert_close(stats[:Co], flat.sum(0), rtol=2e-3, atol=2e-2 * math.sqrt(flat.shape[0]))
+    torch.testing.assert_close(stats[Co:], (flat * flat).sum(0), rtol=5e-3, atol=1e-2)
