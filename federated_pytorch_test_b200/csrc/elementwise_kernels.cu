@@ -81,7 +81,21 @@ col_stats_kernel(const float* __restrict__ y, float* __restrict__ stats, int M, 
   const int cq = threadIdx.x % q, r0 = threadIdx.x / q, rpi = EW_THREADS / q;
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   if (r0 < rpi) {
-    for (int r = blockIdx.x * rpi + r0; r < M; r += gridDim.x * rpi) {
+    const int step = gridDim.x * rpi;
+    int r = blockIdx.x * rpi + r0;
+    // four independent 16-B loads in flight per thread (latency, not bandwidth, bounded the one-row-per-trip loop)
+    for (; r + 3 * step < M; r += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const float4*>(y + size_t(r + u * step) * C)[cq];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s1[0] += v[u].x; s1[1] += v[u].y; s1[2] += v[u].z; s1[3] += v[u].w;
+        s2[0] = fmaf(v[u].x, v[u].x, s2[0]); s2[1] = fmaf(v[u].y, v[u].y, s2[1]);
+        s2[2] = fmaf(v[u].z, v[u].z, s2[2]); s2[3] = fmaf(v[u].w, v[u].w, s2[3]);
+      }
+    }
+    for (; r < M; r += step) {
       const float4 v = reinterpret_cast<const float4*>(y + size_t(r) * C)[cq];
       s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
       s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]); s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
@@ -188,19 +202,26 @@ bn_elu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
   if (r0 < rpi) {
     const float4 mu = reinterpret_cast<const float4*>(mean)[cq];
     const float4 is = reinterpret_cast<const float4*>(invstd)[cq];
-    for (int r = blockIdx.x * rpi + r0; r < M; r += gridDim.x * rpi) {
-      const size_t i = size_t(r) * q + cq;
-      float4 d = reinterpret_cast<const float4*>(dout)[i];
+    const int step = gridDim.x * rpi;
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+    for (int r = blockIdx.x * rpi + r0; r < M; r += 2 * step) {
+      // two rows (six 16-B loads) in flight per thread
+      const bool two = r + step < M;
+      const size_t i0 = size_t(r) * q + cq, i1 = size_t(two ? r + step : r) * q + cq;
+      float4 d0 = reinterpret_cast<const float4*>(dout)[i0], d1 = reinterpret_cast<const float4*>(dout)[i1];
+      const float4 o0 = act ? reinterpret_cast<const float4*>(out)[i0] : one;
+      const float4 o1 = act ? reinterpret_cast<const float4*>(out)[i1] : one;
+      const float4 v0 = reinterpret_cast<const float4*>(y)[i0], v1 = reinterpret_cast<const float4*>(y)[i1];
       if (act) {
-        const float4 o = reinterpret_cast<const float4*>(out)[i];
-        d.x *= elu_grad_from_out(o.x); d.y *= elu_grad_from_out(o.y); d.z *= elu_grad_from_out(o.z); d.w *= elu_grad_from_out(o.w);
+        d0.x *= elu_grad_from_out(o0.x); d0.y *= elu_grad_from_out(o0.y); d0.z *= elu_grad_from_out(o0.z); d0.w *= elu_grad_from_out(o0.w);
+        d1.x *= elu_grad_from_out(o1.x); d1.y *= elu_grad_from_out(o1.y); d1.z *= elu_grad_from_out(o1.z); d1.w *= elu_grad_from_out(o1.w);
       }
-      const float4 v = reinterpret_cast<const float4*>(y)[i];
-      s1[0] += d.x; s1[1] += d.y; s1[2] += d.z; s1[3] += d.w;
-      s2[0] = fmaf(d.x, (v.x - mu.x) * is.x, s2[0]);
-      s2[1] = fmaf(d.y, (v.y - mu.y) * is.y, s2[1]);
-      s2[2] = fmaf(d.z, (v.z - mu.z) * is.z, s2[2]);
-      s2[3] = fmaf(d.w, (v.w - mu.w) * is.w, s2[3]);
+      if (!two) d1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      s1[0] += d0.x + d1.x; s1[1] += d0.y + d1.y; s1[2] += d0.z + d1.z; s1[3] += d0.w + d1.w;
+      s2[0] = fmaf(d0.x, (v0.x - mu.x) * is.x, fmaf(d1.x, (v1.x - mu.x) * is.x, s2[0]));
+      s2[1] = fmaf(d0.y, (v0.y - mu.y) * is.y, fmaf(d1.y, (v1.y - mu.y) * is.y, s2[1]));
+      s2[2] = fmaf(d0.z, (v0.z - mu.z) * is.z, fmaf(d1.z, (v1.z - mu.z) * is.z, s2[2]));
+      s2[3] = fmaf(d0.w, (v0.w - mu.w) * is.w, fmaf(d1.w, (v1.w - mu.w) * is.w, s2[3]));
     }
   }
   float* a = sm + threadIdx.x * 4;

@@ -296,9 +296,38 @@ static void conv3x3_halo(const float* x, const float* w, float* y, float* stats,
 // weight-stationary persistent kernel (conv_ws_tcgen05.cuh): C_out = 64, C_in <= 64, 32-wide maps
 // ------------------------------------------------------------------------------------------------
 static bool ws_applicable(int H, int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil) {
-  if (env_int("FEDB200_WS", 1) == 0) return false;
-  if (kh != 3 || kw != 3 || stride != 1 || pad != 1 || dil != 1) return false;
-  return W == 32 && H >= 4 && C_out == WS_BN && C_in <= 64 && (C_in & 3) == 0;
+  const int mode = env_int("FEDB200_WS", 2);     // 0 off, 1 = 64-channel layers on 32-wide maps, 2 = also 128 ch @ 16
+  if (mode == 0) return false;
+  if (kh != 3 || kw != 3 || stride != 1 || pad != 1 || dil != 1 || (C_in & 3) != 0 || H < 4) return false;
+  if (W == 32 && C_out == 64 && C_in <= 64) return true;
+  if (mode >= 2 && W == 16 && C_out == 128 && C_in <= 128) return true;
+  return false;
+}
+
+template <int BN, int A_SLOT, int MAX_CB>
+static void launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, int tiles, int n_slices,
+                      cudaStream_t stream) {
+  using S = WsSmem<BN, A_SLOT, MAX_CB>;
+  auto kernel = conv3x3_ws_kernel<BN, A_SLOT, MAX_CB>;
+  static int sms = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(ws): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  int per_slice = sms / n_slices;                 // persistent: one CTA per SM, split evenly over the channel slices
+  if (per_slice > tiles) per_slice = tiles;
+  if (per_slice < 1) per_slice = 1;
+  const int grid = per_slice * n_slices;
+  kernel<<<grid, IG_THREADS, S::TOTAL, stream>>>(ta, tb, p, tiles, n_slices);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: ws conv launch: ") + cudaGetErrorString(e));
+  count_launch();
 }
 
 static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
@@ -311,7 +340,7 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   p.a_box_bytes = 128 * p.Wp * p.R;
   p.use_base_offset = 0;
   p.out = y; p.stats = stats;
-  if (p.a_box_bytes > WS_A_SLOT) throw std::runtime_error("fedb200: halo box does not fit its slot (ws)");
+  const int bn = C_out == 64 ? 64 : 32;
   CUtensorMap ta;
   {
     cuuint64_t dims[4] = {cuuint64_t(C_in), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
@@ -323,24 +352,15 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
              "cuTensorMapEncodeTiled(ws)");
   }
-  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(9) * C_in, uint64_t(9) * C_in, WS_BN);
-  static int sms = 0;
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WsSmem::TOTAL);
-    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(ws): ") + cudaGetErrorString(e));
-    configured = true;
-  }
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(9) * C_in, uint64_t(9) * C_in, bn);
   const int tiles = NB * p.tiles_per_img;
-  const int grid = tiles < sms ? tiles : sms;
-  conv3x3_ws_kernel<<<grid, IG_THREADS, WsSmem::TOTAL, stream>>>(ta, tb, p, tiles);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: ws conv launch: ") + cudaGetErrorString(e));
-  count_launch();
+  if (W == 32) {
+    if (p.a_box_bytes > 30720) throw std::runtime_error("fedb200: halo box does not fit its slot (ws32)");
+    launch_ws<64, 30720, 2>(ta, tb, p, tiles, 1, stream);
+  } else {
+    if (p.a_box_bytes > 25600) throw std::runtime_error("fedb200: halo box does not fit its slot (ws16)");
+    launch_ws<32, 25600, 4>(ta, tb, p, tiles, C_out / 32, stream);
+  }
 }
 
 void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
