@@ -22,6 +22,7 @@ struct HaloParams {
   int tiles_per_img;       // ceil(H * Wp / 128)
   int C_in, C_out, cblocks;
   int a_box_bytes;         // 128 * Wp * R
+  int box_h;               // image rows per TMA box (the halo tile is fetched as ceil(R / box_h) boxes issued back to back)
   int use_base_offset;     // experiment switch: encode (addr>>7)&7 in the descriptor's base_offset field
   float* out;              // [NB*H*W, C_out]
   float* stats;            // [2*C_out] or nullptr

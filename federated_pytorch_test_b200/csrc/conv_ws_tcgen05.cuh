@@ -103,7 +103,10 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t ph = (it >> 1) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&a_full[s], uint32_t(p.a_box_bytes));
-          tma_load_4d(a_smem + s * A_SLOT, &tmap_a, &a_full[s], cb * IG_BLOCK_K, -1, hp_a - 1, img);
+          // several small boxes in flight instead of one big one: the TMA unit walks a box row by row (~25 cycles
+          // per 128-B row), but overlaps different boxes.  Rows past R are never read by the MMAs.
+          for (int h = 0; h < p.R; h += p.box_h)
+            tma_load_4d(a_smem + s * A_SLOT + h * p.Wp * 128, &tmap_a, &a_full[s], cb * IG_BLOCK_K, -1, hp_a - 1 + h, img);
         }
       }
     }

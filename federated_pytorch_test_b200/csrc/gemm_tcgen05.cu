@@ -195,9 +195,16 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
   const int bn = pick_block_n(M, N);
   const bool pair = use_pair_kernel(M, bn);
   const int cl = pair ? 2 : pick_cluster(M);
-  CUtensorMap ta = make_tmap_2d(x, M, K, ldx, IG_BLOCK_M);
-  CUtensorMap tb = make_tmap_2d(w, N, K, ldw, bn / cl);
+  const bool subbox = !pair && cl == 1;
+  int box_rows = env_int("FEDB200_TMA_ROWS", 32);          // rows per TMA box (see IgemmParams); >= 128 = one box
+  if (box_rows < 8 || !subbox) box_rows = 1 << 20;
+  const int a_rows = box_rows < IG_BLOCK_M ? box_rows : IG_BLOCK_M;
+  const int b_rows = subbox ? (box_rows < bn ? box_rows : bn) : bn / cl;
+  CUtensorMap ta = make_tmap_2d(x, M, K, ldx, a_rows);
+  CUtensorMap tb = make_tmap_2d(w, N, K, ldw, b_rows);
   IgemmParams p{};
+  p.a_sub = IG_BLOCK_M / a_rows; p.a_sub_rows = a_rows; p.a_sub_h = 1; p.a_rows_per_img = 1 << 20;
+  p.b_sub = subbox ? bn / b_rows : 1; p.b_sub_rows = b_rows;
   p.M = M; p.N = N;
   p.cblocks = (K + IG_BLOCK_K - 1) / IG_BLOCK_K;
   p.num_k_blocks = p.cblocks;
@@ -337,7 +344,10 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   p.R = (p.Wp - 1 + 127 + 2 * p.Wp + 2) / p.Wp + 1;
   p.tiles_per_img = (H * p.Wp + IG_BLOCK_M - 1) / IG_BLOCK_M;
   p.C_in = C_in; p.C_out = C_out; p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
-  p.a_box_bytes = 128 * p.Wp * p.R;
+  p.box_h = env_int("FEDB200_WS_BOXH", 1);
+  if (p.box_h < 1 || p.box_h > p.R) p.box_h = p.R;
+  const int nbox = (p.R + p.box_h - 1) / p.box_h;
+  p.a_box_bytes = 128 * p.Wp * p.box_h * nbox;            // every box delivers box_h full rows (zero-filled outside)
   p.use_base_offset = 0;
   p.out = y; p.stats = stats;
   const int bn = C_out == 64 ? 64 : 32;
@@ -345,7 +355,7 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   {
     cuuint64_t dims[4] = {cuuint64_t(C_in), cuuint64_t(W), cuuint64_t(H), cuuint64_t(NB)};
     cuuint64_t strides[3] = {cuuint64_t(C_in) * 4, cuuint64_t(W) * C_in * 4, cuuint64_t(H) * W * C_in * 4};
-    cuuint32_t box[4] = {uint32_t(IG_BLOCK_K), uint32_t(p.Wp), uint32_t(p.R), 1};
+    cuuint32_t box[4] = {uint32_t(IG_BLOCK_K), uint32_t(p.Wp), uint32_t(p.box_h), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     check_cu(encode_fn()(&ta, tmap_dtype(), 4, const_cast<float*>(x), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -355,10 +365,10 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(9) * C_in, uint64_t(9) * C_in, bn);
   const int tiles = NB * p.tiles_per_img;
   if (W == 32) {
-    if (p.a_box_bytes > 30720) throw std::runtime_error("fedb200: halo box does not fit its slot (ws32)");
+    if (128 * p.Wp * p.box_h * nbox > 30720) p.box_h = p.R, p.a_box_bytes = 128 * p.Wp * p.R;  // keep inside the slot
     launch_ws<64, 30720, 2>(ta, tb, p, tiles, 1, stream);
   } else {
-    if (p.a_box_bytes > 25600) throw std::runtime_error("fedb200: halo box does not fit its slot (ws16)");
+    if (128 * p.Wp * p.box_h * nbox > 25600) p.box_h = p.R, p.a_box_bytes = 128 * p.Wp * p.R;
     launch_ws<32, 25600, 4>(ta, tb, p, tiles, C_out / 32, stream);
   }
 }
@@ -382,9 +392,28 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   const int bn = pick_block_n(M, C_out);
   const bool pair = use_pair_kernel(M, bn);
   const int cl = pair ? 2 : pick_cluster(M);
-  CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
-  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn / cl);
+  const bool subbox = !pair && cl == 1;
+  int box_rows = env_int("FEDB200_TMA_ROWS", 32);
+  if (box_rows < 8 || !subbox) box_rows = 1 << 20;
+  // A sub-box = sub_h consecutive image rows of ONE image (>= 8 pixels so that every box starts on a swizzle atom)
+  int sub_h = box_rows / W_out;
+  if (sub_h < 1) sub_h = 1;
+  if (sub_h > boxH) sub_h = boxH;
+  while (boxH % sub_h) --sub_h;
+  while ((sub_h * W_out) % 8 != 0 && sub_h < boxH) ++sub_h;
+  if (!subbox || (sub_h * W_out) % 8 != 0 || boxH % sub_h) sub_h = boxH;
+  const int b_rows = subbox ? (box_rows < bn ? box_rows : bn) : bn / cl;
+  CUtensorMap ta = subbox ? make_tmap_nhwc(x, NB, H, W, C_in, 1, sub_h, W_out, stride)
+                          : make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, b_rows);
   IgemmParams p{};
+  if (subbox) {
+    p.a_sub = boxN * (boxH / sub_h); p.a_sub_rows = sub_h * W_out; p.a_sub_h = sub_h; p.a_rows_per_img = boxH;
+    p.b_sub = bn / b_rows; p.b_sub_rows = b_rows;
+  } else {
+    p.a_sub = 1; p.a_sub_rows = IG_BLOCK_M; p.a_sub_h = boxH; p.a_rows_per_img = boxH;
+    p.b_sub = 1; p.b_sub_rows = b_rows;
+  }
   p.M = M; p.N = C_out;
   p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
   p.num_k_blocks = kh * kw * p.cblocks;

@@ -41,6 +41,14 @@ struct IgemmParams {
   const float* bias;     // [N] or nullptr
   int act;               // 1 = ELU
   float* stats;          // [2*N]: sum, sumsq per column (atomicAdd) or nullptr
+  // TMA sub-boxes: the TMA unit works through ONE box at ~25 cycles per 128-B row but runs many boxes concurrently
+  // (measured, profiles/ROOFLINE.md), so each operand tile is fetched as several small boxes issued back to back.
+  int a_sub;             // number of A sub-boxes per stage
+  int a_sub_rows;        // tile rows (pixels) per A sub-box
+  int a_sub_h;           // conv: image rows per A sub-box
+  int a_rows_per_img;    // conv: image rows of one image covered by the tile (boxH)
+  int b_sub;             // number of B sub-boxes per stage
+  int b_sub_rows;        // rows (output channels) per B sub-box
   int kb_per_split;      // split-K: CTA z handles k-blocks [z*kb_per_split, ...) and red.adds into a zeroed output
   int k_splits;          // 1 = plain stores (+ fused stats); > 1 = reduction through L2 atomics, stats done by caller
 };
@@ -125,14 +133,21 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int cb = kb - tap * p.cblocks;
         if (p.is_conv) {
           const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
-          tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad,
-                      h_base * p.stride + r * p.dil - p.pad, img);
+          int hrow = 0, dn = 0;                         // image row / image offset of the sub-box inside the tile
+          for (int i = 0; i < p.a_sub; ++i) {
+            tma_load_4d(a_dst + i * p.a_sub_rows * 128, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad,
+                        (h_base + hrow) * p.stride + r * p.dil - p.pad, img + dn);
+            hrow += p.a_sub_h;
+            if (hrow >= p.a_rows_per_img) { hrow = 0; ++dn; }
+          }
         } else {
-          tma_load_2d(a_dst, &tmap_a, &full_bar[s], kb * IG_BLOCK_K, m0);
+          for (int i = 0; i < p.a_sub; ++i)
+            tma_load_2d(a_dst + i * p.a_sub_rows * 128, &tmap_a, &full_bar[s], kb * IG_BLOCK_K, m0 + i * p.a_sub_rows);
         }
         const int b_col = tap * p.b_cols_per_tap + cb * IG_BLOCK_K;
         if (CL == 1) {
-          tma_load_2d(b_dst, &tmap_b, &full_bar[s], b_col, n0);
+          for (int i = 0; i < p.b_sub; ++i)
+            tma_load_2d(b_dst + i * p.b_sub_rows * 128, &tmap_b, &full_bar[s], b_col, n0 + i * p.b_sub_rows);
         } else {
           // my 1/CL slice of the weight tile, written into the same slot of every CTA in the cluster
           tma_load_2d_multicast(b_dst + cta_rank * (B_SLICE_ROWS * IG_BLOCK_K * 4), &tmap_b, &full_bar[s], b_col,

@@ -62,3 +62,48 @@ def test_fused_collectives_across_ranks(tmp_path, world):
     print(rep["transport"], "multicast:", rep["multicast"])
     bad = [c for c in rep["cases"] if not c[2]]
     assert not bad, bad
+
+
+def _engine_worker(rank, world, port, out_dir, K, algo):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from federated_pytorch_test_b200.api import consensus_multi, federated_multi
+
+    mod = federated_multi if algo == "fedavg" else consensus_multi
+    extra = {} if algo == "fedavg" else dict(bb_update=True)
+    lines = []
+    cfg = mod.Config(K=K, Nloop=1, Nadmm=3, max_minibatches=2, check_results=False, save_model=False, train_size=4096,
+                     test_size=128, model="Net", graphs=False, fast=True, collective="fused", **extra)
+    eng = mod.run(cfg, log=lines.append)
+    torch.cuda.synchronize()
+    if rank == 0:
+        torch.save({"lines": lines, "coll": eng.coll.name, "local": [r.ck for r in eng.replicas]}, os.path.join(out_dir, "%s.pt" % algo))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("algo", ["fedavg", "admm"])
+def test_co_resident_replicas_across_ranks_match_single_process(tmp_path, algo):
+    """K = 4 workers on 2 GPUs (two co-resident replicas per rank, fused NVLink aggregation) must reproduce the
+    residual trace of the single-process K = 4 run (the reference's topology)."""
+    import torch.multiprocessing as mp
+    from federated_pytorch_test_b200.api import consensus_multi, federated_multi
+    port = 29800 + (os.getpid() % 1000) + (7 if algo == "admm" else 0)
+    mp.spawn(_engine_worker, args=(2, port, str(tmp_path), 4, algo), nprocs=2, join=True)
+    got = torch.load(str(tmp_path / ("%s.pt" % algo)), weights_only=False)
+    assert got["coll"] == "fused" and got["local"] == [0, 2]
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    mod = federated_multi if algo == "fedavg" else consensus_multi
+    extra = {} if algo == "fedavg" else dict(bb_update=True)
+    lines = []
+    mod.run(mod.Config(K=4, Nloop=1, Nadmm=3, max_minibatches=2, check_results=False, save_model=False, train_size=4096,
+                       test_size=128, model="Net", graphs=False, fast=True, collective="fused", distributed=False, **extra),
+            log=lines.append)
+    key = "dual (" if algo == "fedavg" else "block=["
+    a = [l for l in got["lines"] if l.startswith(key)]
+    b = [l for l in lines if l.startswith(key)]
+    assert len(a) == len(b) == 15
+    for x, y in zip(a, b):
+        vx, vy = float(x.rsplit("=", 1)[1]), float(y.rsplit("=", 1)[1])
+        assert vx == pytest.approx(vy, rel=5e-3, abs=1e-9), (x, y)

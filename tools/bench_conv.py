@@ -16,16 +16,16 @@ SHAPES = [  # name, B, H, Cin, Cout, k, stride, pad
 ]
 BASE = dict(FEDB200_HALO="0", FEDB200_CLUSTER="1", FEDB200_HALO_BO="0", FEDB200_TMAP_F32="0", FEDB200_BLOCK_N="0",
             FEDB200_2CTA="0")
-BASE["FEDB200_SPLITK"] = "1"
-BASE["FEDB200_WS"] = "0"
+BASE.update(FEDB200_SPLITK="0", FEDB200_WS="2", FEDB200_HALO="1", FEDB200_TMA_ROWS="128", FEDB200_WS_BOXH="7")
 VARIANTS = [
-    ("1cta nosplit", {}),
-    ("splitk auto", dict(FEDB200_SPLITK="0")),
-    ("splitk auto bn128", dict(FEDB200_SPLITK="0", FEDB200_BLOCK_N="128")),
-    ("splitk 2", dict(FEDB200_SPLITK="2")),
-    ("splitk 4", dict(FEDB200_SPLITK="4")),
-    ("halo", dict(FEDB200_HALO="1")),
-    ("default(ws)", dict(FEDB200_SPLITK="0", FEDB200_HALO="1", FEDB200_WS="1")),
+    ("one box / operand", {}),
+    ("generic rows32", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_TMA_ROWS="32")),
+    ("generic rows16", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_TMA_ROWS="16")),
+    ("generic rows128", dict(FEDB200_WS="0", FEDB200_HALO="0")),
+    ("ws boxh=4", dict(FEDB200_WS_BOXH="4")),
+    ("ws boxh=2", dict(FEDB200_WS_BOXH="2")),
+    ("ws boxh=1", dict(FEDB200_WS_BOXH="1")),
+    ("default", dict(FEDB200_TMA_ROWS="32", FEDB200_WS_BOXH="1")),
 ]
 
 
