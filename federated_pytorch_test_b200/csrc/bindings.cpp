@@ -107,7 +107,7 @@ void col_stats(Tensor y, Tensor stats) {
 // y, out: [M, C] views of NHWC tensors.  Returns (out, save_mean, save_invstd).
 std::vector<Tensor> bn_elu_fwd(Tensor y, Tensor stats, Tensor gamma, Tensor beta, c10::optional<Tensor> residual,
                                c10::optional<Tensor> running_mean, c10::optional<Tensor> running_var, double eps,
-                               double momentum, bool act) {
+                               double momentum, bool act, bool self_clean) {
   CHECK_F32_CUDA(y); CHECK_CONTIG(y);
   c10::cuda::CUDAGuard guard(y.device());
   const int C = (int)y.size(-1);
@@ -116,8 +116,9 @@ std::vector<Tensor> bn_elu_fwd(Tensor y, Tensor stats, Tensor gamma, Tensor beta
   auto sm = torch::empty({C}, y.options()), si = torch::empty({C}, y.options());
   float* rm = (running_mean.has_value() && running_mean->defined()) ? running_mean->data_ptr<float>() : nullptr;
   float* rv = (running_var.has_value() && running_var->defined()) ? running_var->data_ptr<float>() : nullptr;
-  fb::bn_elu_fwd(fptr(y), fptr(stats), fptr(gamma), fptr(beta), opt_ptr(residual), fptr_mut(out), rm, rv, fptr_mut(sm),
-                 fptr_mut(si), M, C, (float)eps, (float)momentum, act ? 1 : 0, 1, cur_stream());
+  TORCH_CHECK(stats.numel() >= 2 * C + (self_clean ? 1 : 0), "stats buffer too small");
+  fb::bn_elu_fwd(fptr(y), fptr_mut(stats), fptr(gamma), fptr(beta), opt_ptr(residual), fptr_mut(out), rm, rv, fptr_mut(sm),
+                 fptr_mut(si), M, C, (float)eps, (float)momentum, act ? 1 : 0, self_clean ? 1 : 0, cur_stream());
   return {out, sm, si};
 }
 // Returns (dy, dres or undefined); accumulates into dgamma / dbeta when given.

@@ -132,11 +132,12 @@ void col_stats(const float* y, float* stats, int M, int C, cudaStream_t s) {
 }
 
 __global__ void __launch_bounds__(EW_THREADS)
-bn_elu_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, const float* __restrict__ gamma,
+bn_elu_fwd_kernel(const float* __restrict__ y, float* __restrict__ stats, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const float* __restrict__ residual, float* __restrict__ out,
                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
-                  float* __restrict__ save_invstd, int M, int C, float eps, float momentum, int act) {
+                  float* __restrict__ save_invstd, int M, int C, float eps, float momentum, int act, int self_clean) {
   extern __shared__ float sm[];                   // scale[C] | shift[C]
+  __shared__ int last_block;
   float* scale = sm;
   float* shift = sm + C;
   const float invM = 1.f / float(M);
@@ -159,6 +160,20 @@ bn_elu_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, 
     }
   }
   __syncthreads();
+  if (self_clean) {
+    // Every block has now consumed the statistics.  The last one to say so zeroes the accumulators (and the counter
+    // behind them) for the next convolution that uses this buffer: no memset launch per layer, CUDA-graph safe.
+    unsigned int* counter = reinterpret_cast<unsigned int*>(stats + 2 * C);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last_block = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_block) {
+      for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) stats[c] = 0.f;
+      if (threadIdx.x == 0) *counter = 0u;
+    }
+  }
   const int q = C >> 2;
   const size_t total = size_t(M) * q;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -175,18 +190,17 @@ bn_elu_fwd_kernel(const float* __restrict__ y, const float* __restrict__ stats, 
     reinterpret_cast<float4*>(out)[i] = o;
   }
 }
-void bn_elu_fwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* residual,
+void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* beta, const float* residual,
                 float* out, float* running_mean, float* running_var, float* save_mean, float* save_invstd, int M, int C,
-                float eps, float momentum, int act, int training, cudaStream_t s) {
+                float eps, float momentum, int act, int self_clean, cudaStream_t s) {
   if (C & 3) throw std::runtime_error("fedb200: bn_elu_fwd needs C % 4 == 0");
-  (void)training;
   const size_t total = size_t(M) * (C >> 2);
   int grid = int((total + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
   if (grid > sm_count() * 8) grid = sm_count() * 8;
   if (grid < 1) grid = 1;
   bn_elu_fwd_kernel<<<grid, EW_THREADS, 2 * C * sizeof(float), s>>>(y, stats, gamma, beta, residual, out, running_mean,
                                                                     running_var, save_mean, save_invstd, M, C, eps,
-                                                                    momentum, act);
+                                                                    momentum, act, self_clean);
   check_launch("bn_elu_fwd");
 }
 

@@ -38,9 +38,10 @@ size_t lbfgs_two_loop_work_floats(int k);
 void normalize_u8_nhwc(const uint8_t* in, float* out, int npix, int c_out, const float* mean3, const float* std3,
                        int to_nchw, int H, int W, cudaStream_t s);
 void col_stats(const float* y, float* stats, int M, int C, cudaStream_t s);
-void bn_elu_fwd(const float* y, const float* stats, const float* gamma, const float* beta, const float* residual,
+// stats: [2C] sums (+ one uint counter behind them when self_clean: the kernel zeroes the buffer after the last read)
+void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* beta, const float* residual,
                 float* out, float* running_mean, float* running_var, float* save_mean, float* save_invstd, int M, int C,
-                float eps, float momentum, int act, int training, cudaStream_t s);
+                float eps, float momentum, int act, int self_clean, cudaStream_t s);
 void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
                        float* sums, int M, int C, int act, cudaStream_t s);
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,

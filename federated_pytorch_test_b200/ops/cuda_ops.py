@@ -153,11 +153,26 @@ def conv_bn_act_supported(x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d) 
 
 
 _FLIP_CACHE = {}
+_STATS_BUFFERS = {}
+
+
+def _stats_buffer(weight: torch.Tensor, C: int):
+    """Per-layer BatchNorm accumulator ``[sum | sumsq | counter]``: zeroed once at allocation, then kept clean by
+    ``bn_elu_fwd`` itself (its last block re-zeroes it), so no fill kernel is launched per convolution."""
+    key = (weight.data_ptr(), C)
+    buf = _STATS_BUFFERS.get(key)
+    if buf is None:
+        if torch.cuda.is_current_stream_capturing():   # graph-pool memory must not be cached
+            return torch.zeros(2 * C + 1, dtype=torch.float32, device=weight.device), False
+        buf = torch.zeros(2 * C + 1, dtype=torch.float32, device=weight.device)
+        _STATS_BUFFERS[key] = buf
+    return buf, True
 
 
 def clear_caches() -> None:
     """Drop cached derived tensors (call after loading a checkpoint into existing parameters)."""
     _FLIP_CACHE.clear()
+    _STATS_BUFFERS.clear()
 
 
 def _flipped_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
@@ -188,10 +203,10 @@ class _ConvBnAct(torch.autograd.Function):
             xn = F.pad(xn, (0, 1))
             wk = F.pad(wk, (0, 1))
         Co = weight.shape[0]
-        stats = torch.zeros(2 * Co, dtype=torch.float32, device=x.device)
+        stats, self_clean = _stats_buffer(weight, Co)
         y = e.conv2d_nhwc(xn, wk, stats, stride, pad, 1)
         res = _nhwc(residual) if residual is not None else None
-        out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, res, running_mean, running_var, eps, momentum, act)
+        out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, res, running_mean, running_var, eps, momentum, act, self_clean)
         ctx.save_for_backward(xn, wk, y, out, mean, invstd, gamma)
         ctx.cfg = (stride, pad, act, residual is not None, tuple(weight.shape), x.shape[1])
         return out.permute(0, 3, 1, 2)

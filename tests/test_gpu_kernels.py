@@ -207,7 +207,9 @@ def test_bn_elu_forward_backward(C, M, res, act):
     stats = torch.zeros(2 * C, device=DEV)
     e.col_stats(y, stats)
     torch.testing.assert_close(stats[:C], y.sum(0), rtol=1e-4, atol=1e-2)
-    out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, r, rm, rv, 1e-5, 0.1, act)
+    stats = torch.cat([stats, torch.zeros(1, device=DEV)])      # [sum | sumsq | block counter]
+    out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, r, rm, rv, 1e-5, 0.1, act, True)
+    assert float(stats.abs().sum()) == 0.0, "the kernel must leave its accumulator clean for the next use"
     # oracle
     yr, gr, br = y.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
     rr = r.clone().requires_grad_() if res else None
