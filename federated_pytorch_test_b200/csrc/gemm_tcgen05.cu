@@ -196,7 +196,7 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
   const bool pair = use_pair_kernel(M, bn);
   const int cl = pair ? 2 : pick_cluster(M);
   const bool subbox = !pair && cl == 1;
-  int box_rows = env_int("FEDB200_TMA_ROWS", 32);          // rows per TMA box (see IgemmParams); >= 128 = one box
+  int box_rows = env_int("FEDB200_TMA_ROWS", 128);          // rows per TMA box (see IgemmParams); >= 128 = one box
   if (box_rows < 8 || !subbox) box_rows = 1 << 20;
   const int a_rows = box_rows < IG_BLOCK_M ? box_rows : IG_BLOCK_M;
   const int b_rows = subbox ? (box_rows < bn ? box_rows : bn) : bn / cl;
@@ -303,7 +303,7 @@ static void conv3x3_halo(const float* x, const float* w, float* y, float* stats,
 // weight-stationary persistent kernel (conv_ws_tcgen05.cuh): C_out = 64, C_in <= 64, 32-wide maps
 // ------------------------------------------------------------------------------------------------
 static bool ws_applicable(int H, int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil) {
-  const int mode = env_int("FEDB200_WS", 2);     // 0 off, 1 = 64-channel layers on 32-wide maps, 2 = also 128 ch @ 16
+  const int mode = env_int("FEDB200_WS", 1);     // 0 off, 1 = 64-channel layers on 32-wide maps, 2 = also 128 ch @ 16
   if (mode == 0) return false;
   if (kh != 3 || kw != 3 || stride != 1 || pad != 1 || dil != 1 || (C_in & 3) != 0 || H < 4) return false;
   if (W == 32 && C_out == 64 && C_in <= 64) return true;
@@ -344,8 +344,10 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   p.R = (p.Wp - 1 + 127 + 2 * p.Wp + 2) / p.Wp + 1;
   p.tiles_per_img = (H * p.Wp + IG_BLOCK_M - 1) / IG_BLOCK_M;
   p.C_in = C_in; p.C_out = C_out; p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
-  p.box_h = env_int("FEDB200_WS_BOXH", 1);
+  p.box_h = env_int("FEDB200_WS_BOXH", 0);
   if (p.box_h < 1 || p.box_h > p.R) p.box_h = p.R;
+  const int slot_bytes = W == 32 ? 30720 : 25600;
+  if (128 * p.Wp * p.box_h * ((p.R + p.box_h - 1) / p.box_h) > slot_bytes) p.box_h = p.R;   // keep inside the slot
   const int nbox = (p.R + p.box_h - 1) / p.box_h;
   p.a_box_bytes = 128 * p.Wp * p.box_h * nbox;            // every box delivers box_h full rows (zero-filled outside)
   p.use_base_offset = 0;
@@ -365,10 +367,8 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(9) * C_in, uint64_t(9) * C_in, bn);
   const int tiles = NB * p.tiles_per_img;
   if (W == 32) {
-    if (128 * p.Wp * p.box_h * nbox > 30720) p.box_h = p.R, p.a_box_bytes = 128 * p.Wp * p.R;  // keep inside the slot
     launch_ws<64, 30720, 2>(ta, tb, p, tiles, 1, stream);
   } else {
-    if (128 * p.Wp * p.box_h * nbox > 25600) p.box_h = p.R, p.a_box_bytes = 128 * p.Wp * p.R;
     launch_ws<32, 25600, 4>(ta, tb, p, tiles, C_out / 32, stream);
   }
 }
@@ -393,7 +393,7 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   const bool pair = use_pair_kernel(M, bn);
   const int cl = pair ? 2 : pick_cluster(M);
   const bool subbox = !pair && cl == 1;
-  int box_rows = env_int("FEDB200_TMA_ROWS", 32);
+  int box_rows = env_int("FEDB200_TMA_ROWS", 128);
   if (box_rows < 8 || !subbox) box_rows = 1 << 20;
   // A sub-box = sub_h consecutive image rows of ONE image (>= 8 pixels so that every box starts on a swizzle atom)
   int sub_h = box_rows / W_out;

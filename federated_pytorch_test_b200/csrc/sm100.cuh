@@ -52,13 +52,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 // Bounded wait: a protocol bug must trap (error returned to the host) instead of hanging the GPU.
+static __device__ int g_mbar_timeout_reported = 0;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("fedb200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, parity);
+      if (atomicExch(&g_mbar_timeout_reported, 1) == 0)     // one line per process, not one per CTA
+        printf("fedb200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, parity);
       __trap();
     }
   }

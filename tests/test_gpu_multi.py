@@ -53,7 +53,7 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", sorted({2, min(8, torch.cuda.device_count() if torch.cuda.is_available() else 2)}))
 def test_fused_collectives_across_ranks(tmp_path, world):
     import torch.multiprocessing as mp
     port = 29700 + (os.getpid() % 1000)

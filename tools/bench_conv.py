@@ -22,10 +22,10 @@ VARIANTS = [
     ("generic rows32", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_TMA_ROWS="32")),
     ("generic rows16", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_TMA_ROWS="16")),
     ("generic rows128", dict(FEDB200_WS="0", FEDB200_HALO="0")),
-    ("ws boxh=4", dict(FEDB200_WS_BOXH="4")),
+    ("ws boxh=3", dict(FEDB200_WS_BOXH="3")),
     ("ws boxh=2", dict(FEDB200_WS_BOXH="2")),
     ("ws boxh=1", dict(FEDB200_WS_BOXH="1")),
-    ("default", dict(FEDB200_TMA_ROWS="32", FEDB200_WS_BOXH="1")),
+    ("auto split-K", dict(FEDB200_SPLITK="-1")),
 ]
 
 
