@@ -102,6 +102,7 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int s = it & 1;
           const uint32_t ph = (it >> 1) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
+          if (p.dbg & 1) { mbar_arrive(&a_full[s]); continue; }
           mbar_arrive_expect_tx(&a_full[s], uint32_t(p.a_box_bytes));
           // several small boxes in flight instead of one big one: the TMA unit walks a box row by row (~25 cycles
           // per 128-B row), but overlaps different boxes.  Rows past R are never read by the MMAs.
@@ -113,37 +114,48 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BN);
-    if (my_tiles > 0) mbar_wait(w_full, 0);
-    int it = 0;
-    for (int j = 0; j < my_tiles; ++j) {
-      const int tile = tile0 + j * tstride;
-      const int img = tile / p.tiles_per_img;
-      const int u0 = (tile - img * p.tiles_per_img) * IG_BLOCK_M;
-      const int row_off0 = u0 - (u0 / p.Wp) * p.Wp;
-      const int acc = j & 1;
-      mbar_wait(&t_empty[acc], ((j >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
-      tc_fence_after();
-      for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
-        const int s = it & 1;
-        mbar_wait(&a_full[s], (it >> 1) & 1);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = smem_u32(a_smem + s * A_SLOT);
-          const uint32_t b_base = smem_u32(w_smem + cb * 9 * S::W_TILE);
-#pragma unroll 1
-          for (int t = 0; t < 9; ++t) {
-            const int r = t / 3, sx = t - 3 * r;
-            const uint64_t adesc = make_kmajor_sw128_desc(a_base + uint32_t(row_off0 + r * p.Wp + sx) * 128u);
-            const uint64_t bdesc = make_kmajor_sw128_desc(b_base + uint32_t(t) * S::W_TILE);
+    // ONE thread runs the whole issue loop.  Its scalar instructions are on the critical path (a lone thread issues
+    // roughly one dependent instruction every 5-10 cycles, and a 128x64x8 MMA only lasts 48 cycles: measured in
+    // tools/probe_mma.cu), so the loop is kept free of divisions and descriptor rebuilds: all 36 MMAs of a
+    // (tile, channel block) are unrolled and every descriptor is base + compile-time/loop-invariant offset.
+    if (lane == 0 && my_tiles > 0) {
+      mbar_wait(w_full, 0);
+      uint32_t tap_off[9];                                   // (r * Wp + sx) pixel rows of 128 B, encoded >> 4
 #pragma unroll
-            for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k)
-              umma_tf32(tmem_base + uint32_t(acc * BN), adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
-                        (cb | t | k) != 0 ? 1u : 0u);
+      for (int t = 0; t < 9; ++t) tap_off[t] = (p.dbg & 8) ? 0u : uint32_t((t / 3) * p.Wp + (t % 3)) * 8u;
+      const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(a_smem));
+      const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(w_smem));
+      uint32_t s = 0, a_ph = 0;
+      for (int j = 0; j < my_tiles; ++j) {
+        const int tile = tile0 + j * tstride;
+        const int img = tile / p.tiles_per_img;
+        const int u0 = (tile - img * p.tiles_per_img) * IG_BLOCK_M;
+        const uint32_t row_off0 = uint32_t(u0 - (u0 / p.Wp) * p.Wp);
+        const uint32_t acc = uint32_t(j & 1);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        mbar_wait(&t_empty[acc], ((j >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(&a_full[s], a_ph);
+          tc_fence_after();
+          const uint64_t ad = a_desc0 + uint64_t(s * (A_SLOT >> 4) + row_off0 * 8u);
+          const uint64_t bd = b_desc0 + uint64_t(uint32_t(cb) * 9u * (S::W_TILE >> 4));
+          if (!(p.dbg & 2)) {
+            umma_tf32(d_tmem, ad + tap_off[0], bd, idesc, cb != 0 ? 1u : 0u);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+#pragma unroll
+              for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+                if (t == 0 && k == 0) continue;
+                umma_tf32_acc(d_tmem, ad + uint64_t(tap_off[t] + 2 * k), bd + uint64_t(t * (S::W_TILE >> 4) + 2 * k), idesc);
+              }
+            }
           }
           umma_commit(&a_empty[s]);
           if (cb == p.cblocks - 1) umma_commit(&t_full[acc]);
+          s ^= 1;
+          a_ph ^= (s == 0);
         }
-        __syncwarp();
       }
     }
   } else {
@@ -183,7 +195,7 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int r = i * 4 + (lane >> 3), cq = lane & 7;
           const int off = __shfl_sync(0xffffffffu, out_off, r);
           const float4 val = *reinterpret_cast<const float4*>(my_scratch + r * WS_SCR_LD + cq * 4);
-          if (off >= 0) *reinterpret_cast<float4*>(p.out + off + c0 + cq * 4) = val;
+          if (off >= 0 && !(p.dbg & 4)) *reinterpret_cast<float4*>(p.out + off + c0 + cq * 4) = val;
         }
         if (p.stats != nullptr) {
           float s1 = 0.f, s2 = 0.f;

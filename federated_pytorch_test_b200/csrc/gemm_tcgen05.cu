@@ -77,10 +77,10 @@ static CUtensorMap make_tmap_nhwc(const float* ptr, uint64_t N, uint64_t H, uint
   return m;
 }
 
-template <int BN, int ST, int CL>
+template <int BN, int ST, int CL, int KPS>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
-  using S = IgemmSmem<BN, ST>;
-  auto kernel = igemm_tf32_kernel<BN, ST, CL>;
+  using S = IgemmSmem<BN, ST, KPS>;
+  auto kernel = igemm_tf32_kernel<BN, ST, CL, KPS>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -105,25 +105,28 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmPara
   count_launch();
 }
 
-template <int BN, int ST>
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+// KPS = 1 keeps one k-block (4 MMAs) per barrier round trip (first version, kept for A/B runs: FEDB200_KPS=1) and is
+// what the cluster-multicast experiments use; KPS = 2 (default) halves the number of round trips.
+template <int BN, int ST1, int ST2>
 static void dispatch_cl(int cl, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
-  if (cl >= 4) launch<BN, ST, 4>(ta, tb, p, s);
-  else if (cl == 2) launch<BN, ST, 2>(ta, tb, p, s);
-  else launch<BN, ST, 1>(ta, tb, p, s);
+  if (cl >= 4) launch<BN, ST1, 4, 1>(ta, tb, p, s);
+  else if (cl == 2) launch<BN, ST1, 2, 1>(ta, tb, p, s);
+  else if (env_int("FEDB200_KPS", 2) == 1) launch<BN, ST1, 1, 1>(ta, tb, p, s);
+  else launch<BN, ST2, 1, 2>(ta, tb, p, s);
 }
 
 static void dispatch(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
   switch (bn) {
-    case 32: dispatch_cl<32, 8>(cl, ta, tb, p, s); break;
-    case 64: dispatch_cl<64, 6>(cl, ta, tb, p, s); break;
-    case 128: dispatch_cl<128, 5>(cl, ta, tb, p, s); break;
-    default: dispatch_cl<256, 4>(cl, ta, tb, p, s); break;
+    case 32: dispatch_cl<32, 8, 4>(cl, ta, tb, p, s); break;
+    case 64: dispatch_cl<64, 6, 4>(cl, ta, tb, p, s); break;
+    case 128: dispatch_cl<128, 5, 3>(cl, ta, tb, p, s); break;
+    default: dispatch_cl<256, 4, 2>(cl, ta, tb, p, s); break;
   }
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
 }
 
 // ---- CTA-pair kernel (igemm2_tcgen05.cuh): 256 x BN tile per pair of SMs ----
@@ -195,22 +198,15 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
   const int bn = pick_block_n(M, N);
   const bool pair = use_pair_kernel(M, bn);
   const int cl = pair ? 2 : pick_cluster(M);
-  const bool subbox = !pair && cl == 1;
-  int box_rows = env_int("FEDB200_TMA_ROWS", 128);          // rows per TMA box (see IgemmParams); >= 128 = one box
-  if (box_rows < 8 || !subbox) box_rows = 1 << 20;
-  const int a_rows = box_rows < IG_BLOCK_M ? box_rows : IG_BLOCK_M;
-  const int b_rows = subbox ? (box_rows < bn ? box_rows : bn) : bn / cl;
-  CUtensorMap ta = make_tmap_2d(x, M, K, ldx, a_rows);
-  CUtensorMap tb = make_tmap_2d(w, N, K, ldw, b_rows);
+  CUtensorMap ta = make_tmap_2d(x, M, K, ldx, IG_BLOCK_M);
+  CUtensorMap tb = make_tmap_2d(w, N, K, ldw, bn / cl);
   IgemmParams p{};
-  p.a_sub = IG_BLOCK_M / a_rows; p.a_sub_rows = a_rows; p.a_sub_h = 1; p.a_rows_per_img = 1 << 20;
-  p.b_sub = subbox ? bn / b_rows : 1; p.b_sub_rows = b_rows;
   p.M = M; p.N = N;
   p.cblocks = (K + IG_BLOCK_K - 1) / IG_BLOCK_K;
   p.num_k_blocks = p.cblocks;
   p.taps_w = 1; p.b_cols_per_tap = 0; p.is_conv = 0;
   p.out = out; p.ldo = ldo; p.bias = bias; p.act = act; p.stats = nullptr;
-  p.k_splits = 1; p.kb_per_split = p.num_k_blocks;
+  p.k_splits = 1; p.kb_per_split = p.num_k_blocks; p.dbg = env_int("FEDB200_DBG", 0);
   if (pair) dispatch2(bn, ta, tb, p, stream); else dispatch(bn, cl, ta, tb, p, stream);
 }
 
@@ -350,7 +346,7 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   if (128 * p.Wp * p.box_h * ((p.R + p.box_h - 1) / p.box_h) > slot_bytes) p.box_h = p.R;   // keep inside the slot
   const int nbox = (p.R + p.box_h - 1) / p.box_h;
   p.a_box_bytes = 128 * p.Wp * p.box_h * nbox;            // every box delivers box_h full rows (zero-filled outside)
-  p.use_base_offset = 0;
+  p.use_base_offset = 0; p.dbg = env_int("FEDB200_DBG", 0);
   p.out = y; p.stats = stats;
   const int bn = C_out == 64 ? 64 : 32;
   CUtensorMap ta;
@@ -392,28 +388,11 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   const int bn = pick_block_n(M, C_out);
   const bool pair = use_pair_kernel(M, bn);
   const int cl = pair ? 2 : pick_cluster(M);
-  const bool subbox = !pair && cl == 1;
-  int box_rows = env_int("FEDB200_TMA_ROWS", 128);
-  if (box_rows < 8 || !subbox) box_rows = 1 << 20;
-  // A sub-box = sub_h consecutive image rows of ONE image (>= 8 pixels so that every box starts on a swizzle atom)
-  int sub_h = box_rows / W_out;
-  if (sub_h < 1) sub_h = 1;
-  if (sub_h > boxH) sub_h = boxH;
-  while (boxH % sub_h) --sub_h;
-  while ((sub_h * W_out) % 8 != 0 && sub_h < boxH) ++sub_h;
-  if (!subbox || (sub_h * W_out) % 8 != 0 || boxH % sub_h) sub_h = boxH;
-  const int b_rows = subbox ? (box_rows < bn ? box_rows : bn) : bn / cl;
-  CUtensorMap ta = subbox ? make_tmap_nhwc(x, NB, H, W, C_in, 1, sub_h, W_out, stride)
-                          : make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
-  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, b_rows);
+  // one TMA box per operand and k-block: splitting a tile into several smaller boxes was measured SLOWER
+  // (profiles/r1_run10_tma_subbox.log)
+  CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn / cl);
   IgemmParams p{};
-  if (subbox) {
-    p.a_sub = boxN * (boxH / sub_h); p.a_sub_rows = sub_h * W_out; p.a_sub_h = sub_h; p.a_rows_per_img = boxH;
-    p.b_sub = bn / b_rows; p.b_sub_rows = b_rows;
-  } else {
-    p.a_sub = 1; p.a_sub_rows = IG_BLOCK_M; p.a_sub_h = boxH; p.a_rows_per_img = boxH;
-    p.b_sub = 1; p.b_sub_rows = b_rows;
-  }
   p.M = M; p.N = C_out;
   p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
   p.num_k_blocks = kh * kw * p.cblocks;
@@ -421,7 +400,7 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   p.HW_out = H_out * W_out; p.W_out = W_out;
   p.stride = stride; p.pad = pad; p.dil = dil;
   p.out = y; p.ldo = C_out; p.bias = nullptr; p.act = 0; p.stats = stats;
-  p.k_splits = 1; p.kb_per_split = p.num_k_blocks;
+  p.k_splits = 1; p.kb_per_split = p.num_k_blocks; p.dbg = env_int("FEDB200_DBG", 0);
   // Split-K: the kernel is bound by what ONE SM can ingest (~40-60 B/cycle, profiles/r1_run8_*), so a grid that
   // leaves SMs idle (64 CTAs for layer3, 32 for layer4 with 128x256 tiles) wastes most of the chip.  Slice K until
   // ~one full wave of CTAs exists; partial tiles are reduced with red.global.add.v4 into a zeroed output and the

@@ -41,44 +41,43 @@ struct IgemmParams {
   const float* bias;     // [N] or nullptr
   int act;               // 1 = ELU
   float* stats;          // [2*N]: sum, sumsq per column (atomicAdd) or nullptr
-  // TMA sub-boxes: the TMA unit works through ONE box at ~25 cycles per 128-B row but runs many boxes concurrently
-  // (measured, profiles/ROOFLINE.md), so each operand tile is fetched as several small boxes issued back to back.
-  int a_sub;             // number of A sub-boxes per stage
-  int a_sub_rows;        // tile rows (pixels) per A sub-box
-  int a_sub_h;           // conv: image rows per A sub-box
-  int a_rows_per_img;    // conv: image rows of one image covered by the tile (boxH)
-  int b_sub;             // number of B sub-boxes per stage
-  int b_sub_rows;        // rows (output channels) per B sub-box
   int kb_per_split;      // split-K: CTA z handles k-blocks [z*kb_per_split, ...) and red.adds into a zeroed output
   int k_splits;          // 1 = plain stores (+ fused stats); > 1 = reduction through L2 atomics, stats done by caller
+  int dbg;               // profiling ablations (FEDB200_DBG, results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no stores
 };
 
-template <int BLOCK_N, int STAGES>
+// KPS = k-blocks (of 32 fp32 = one 128-B swizzle row) per pipeline stage.  One producer/consumer barrier round trip
+// costs the MMA-issuing thread ~300 cycles that do NOT overlap with MMA execution unless >= 8 MMAs are queued behind
+// it (tools/probe_ring.cu: 4 MMAs of 128x128x8 per handshake run at 38% of the tensor-pipe rate, 8 at 62%), so a
+// stage carries KPS * 4 MMAs.
+template <int BLOCK_N, int STAGES, int KPS>
 struct IgemmSmem {
   static constexpr int A_BYTES = IG_BLOCK_M * IG_BLOCK_K * 4;   // 16 KB
   static constexpr int B_BYTES = BLOCK_N * IG_BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int KB_BYTES = A_BYTES + B_BYTES;            // one k-block: [A | B]
+  static constexpr int STAGE_BYTES = KPS * KB_BYTES;
   static constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;         // per-epilogue-warp transpose tiles
   static constexpr int PART_BYTES = 4 * BLOCK_N * 2 * 4;        // per-warp column partials (sum, sumsq)
   static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + PART_BYTES + BAR_BYTES + 1024;  // + align slack
 };
 
-template <int BLOCK_N, int STAGES, int CL>
+template <int BLOCK_N, int STAGES, int CL, int KPS>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const IgemmParams p) {
-  using S = IgemmSmem<BLOCK_N, STAGES>;
+  using S = IgemmSmem<BLOCK_N, STAGES, KPS>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N must be a multiple of 32 in [32,256]");
   static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size 1, 2 or 4");
   static_assert((BLOCK_N / CL) % 8 == 0, "each CTA's slice of the weight tile must be whole swizzle atoms");
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // power of two >= 32 for 32/64/128/256
   constexpr int B_SLICE_ROWS = BLOCK_N / CL;
   constexpr uint16_t CL_MASK = uint16_t((1u << CL) - 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tiles = smem;                                           // STAGES x [A | B], each 1024-B aligned
+  uint8_t* tiles = smem;                                           // STAGES x KPS x [A | B], each 1024-B aligned
   float* scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
   float* part = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::SCRATCH_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::SCRATCH_BYTES + S::PART_BYTES);
@@ -93,6 +92,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
   const int kb_begin = blockIdx.z * p.kb_per_split;                 // split-K slice of this CTA
   const int kb_count = min(p.kb_per_split, p.num_k_blocks - kb_begin);
+  const int n_iters = (kb_count + KPS - 1) / KPS;                   // pipeline stages this CTA consumes
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -114,70 +114,89 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread; no divisions inside the loop) =====================
     if (lane == 0) {
-      int img = 0, h_base = 0;
+      int img = 0, h0 = 0;
       if (p.is_conv) {
         img = m0 / p.HW_out;
-        h_base = (m0 % p.HW_out) / p.W_out;
+        h0 = ((m0 - img * p.HW_out) / p.W_out) * p.stride - p.pad;
       }
-      for (int it = 0; it < kb_count; ++it) {
-        const int kb = kb_begin + it;
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      int tap = kb_begin / p.cblocks;
+      int cb = kb_begin - tap * p.cblocks;
+      int r = tap / p.taps_w, sx = tap - r * p.taps_w;
+      int s = 0;
+      uint32_t ph = 0;
+      int left = kb_count;
+      for (int it = 0; it < n_iters; ++it) {
+        const int nk = left < KPS ? left : KPS;
+        left -= nk;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* a_dst = tiles + s * S::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + S::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        const int tap = kb / p.cblocks;
-        const int cb = kb - tap * p.cblocks;
-        if (p.is_conv) {
-          const int r = tap / p.taps_w, sx = tap - r * p.taps_w;
-          int hrow = 0, dn = 0;                         // image row / image offset of the sub-box inside the tile
-          for (int i = 0; i < p.a_sub; ++i) {
-            tma_load_4d(a_dst + i * p.a_sub_rows * 128, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad,
-                        (h_base + hrow) * p.stride + r * p.dil - p.pad, img + dn);
-            hrow += p.a_sub_h;
-            if (hrow >= p.a_rows_per_img) { hrow = 0; ++dn; }
+        uint8_t* dst = tiles + s * S::STAGE_BYTES;
+        if (p.dbg & 1) {
+          mbar_arrive(&full_bar[s]);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[s], uint32_t(nk * S::KB_BYTES));
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) {
+              uint8_t* a_dst = dst + j * S::KB_BYTES;
+              uint8_t* b_dst = a_dst + S::A_BYTES;
+              if (p.is_conv)
+                tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad, h0 + r * p.dil, img);
+              else
+                tma_load_2d(a_dst, &tmap_a, &full_bar[s], (kb_begin + it * KPS + j) * IG_BLOCK_K, m0);
+              const int b_col = (r * p.taps_w + sx) * p.b_cols_per_tap + cb * IG_BLOCK_K;
+              if (CL == 1) {
+                tma_load_2d(b_dst, &tmap_b, &full_bar[s], b_col, n0);
+              } else {
+                // my 1/CL slice of the weight tile, written into the same slot of every CTA in the cluster
+                tma_load_2d_multicast(b_dst + cta_rank * (B_SLICE_ROWS * IG_BLOCK_K * 4), &tmap_b, &full_bar[s], b_col,
+                                      n0 + int(cta_rank) * B_SLICE_ROWS, CL_MASK);
+              }
+              if (++cb == p.cblocks) {
+                cb = 0;
+                if (++sx == p.taps_w) { sx = 0; ++r; }
+              }
+            }
           }
-        } else {
-          for (int i = 0; i < p.a_sub; ++i)
-            tma_load_2d(a_dst + i * p.a_sub_rows * 128, &tmap_a, &full_bar[s], kb * IG_BLOCK_K, m0 + i * p.a_sub_rows);
         }
-        const int b_col = tap * p.b_cols_per_tap + cb * IG_BLOCK_K;
-        if (CL == 1) {
-          for (int i = 0; i < p.b_sub; ++i)
-            tma_load_2d(b_dst + i * p.b_sub_rows * 128, &tmap_b, &full_bar[s], b_col, n0 + i * p.b_sub_rows);
-        } else {
-          // my 1/CL slice of the weight tile, written into the same slot of every CTA in the cluster
-          tma_load_2d_multicast(b_dst + cta_rank * (B_SLICE_ROWS * IG_BLOCK_K * 4), &tmap_b, &full_bar[s], b_col,
-                                n0 + int(cta_rank) * B_SLICE_ROWS, CL_MASK);
-        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (one thread) =====================
     constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BLOCK_N);
-    for (int it = 0; it < kb_count; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + s * S::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + S::A_BYTES;
-        const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
+    if (lane == 0) {
+      const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(tiles));
+      int s = 0;
+      uint32_t ph = 0;
+      int left = kb_count;
+      for (int it = 0; it < n_iters; ++it) {
+        const int nk = left < KPS ? left : KPS;
+        left -= nk;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t sd = desc0 + uint64_t(uint32_t(s) * uint32_t(S::STAGE_BYTES >> 4));
+        if (!(p.dbg & 2)) {
 #pragma unroll
-        for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
-          // advance along K inside the 128-B swizzle atom: +32 B per step (encoded >>4 => +2)
-          umma_tf32(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (it | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < KPS; ++j) {
+            if (j < nk) {
+              const uint64_t adesc = sd + uint64_t(j * (S::KB_BYTES >> 4));
+              const uint64_t bdesc = adesc + uint64_t(S::A_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+                // advance along K inside the 128-B swizzle atom: +32 B per step (encoded >>4 => +2)
+                if (j == 0 && k == 0) umma_tf32(tmem_base, adesc, bdesc, idesc, it != 0 ? 1u : 0u);
+                else umma_tf32_acc(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc);
+              }
+            }
+          }
         }
         // free the smem slot (in every CTA of the cluster) when these MMAs retire
         if (CL == 1) umma_commit(&empty_bar[s]); else umma_commit_multicast(&empty_bar[s], CL_MASK);
-        if (it == kb_count - 1) umma_commit(tmem_full_bar);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
+      umma_commit(tmem_full_bar);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -202,7 +221,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (p.act) x = elu1(x);
         f[j] = x;
       }
-      if (row_ok) {
+      if (row_ok && !(p.dbg & 4)) {
         float* dst = p.out + size_t(row) * p.ldo + n0 + c0;
         if (p.k_splits > 1) {
           // partial sums of this K slice: vector reduction into the (pre-zeroed) output, resolved in L2

@@ -52,18 +52,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return done != 0;
 }
 // Bounded wait: a protocol bug must trap (error returned to the host) instead of hanging the GPU.
-static __device__ int g_mbar_timeout_reported = 0;
+// The loop is hand-written PTX: try_wait sleeps in hardware until the phase completes or a time limit passes, so the
+// loop body runs a handful of times; a C++ loop around mbar_try_wait with clock64()/printf bookkeeping measured
+// 196 cycles per already-complete wait against 60 for this form (tools/probe_ring.cu, profiles/r1_run12_*).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      if (atomicExch(&g_mbar_timeout_reported, 1) == 0)     // one line per process, not one per CTA
-        printf("fedb200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-               threadIdx.x, parity);
-      __trap();
-    }
-  }
+  // The retry counter lives in an asm-local register: as a C "+r" operand it may share a register with `parity`
+  // (both are 0 on entry for constant-parity waits) and the first failed try would then flip the parity waited on.
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t.reg .b32 T;\n\t"
+      "mov.u32 T, 0;\n\t"
+      "MBW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra MBD_%=;\n\t"
+      "add.u32 T, T, 1;\n\t"
+      "setp.lt.u32 P1, T, 0x1000000;\n\t"
+      "@P1 bra MBW_%=;\n\t"
+      "trap;\n\t"
+      "MBD_%=:\n\t}\n"
+      :
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 
 // ---------------------------------------------------------------- TMA
@@ -127,6 +135,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// accumulate variant with the enable-input-d predicate folded at compile time (one instruction per MMA in the
+// issuing thread: that thread's scalar work is on the critical path, see tools/probe_mma.cu)
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
       : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
