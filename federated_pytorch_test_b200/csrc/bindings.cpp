@@ -122,20 +122,25 @@ std::vector<Tensor> bn_elu_fwd(Tensor y, Tensor stats, Tensor gamma, Tensor beta
   return {out, sm, si};
 }
 // Returns (dy, dres or undefined); accumulates into dgamma / dbeta when given.
-std::vector<Tensor> bn_elu_bwd(Tensor dout, Tensor out, Tensor y, Tensor mean, Tensor invstd, Tensor gamma,
-                               c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta, bool want_dres, bool act) {
-  CHECK_F32_CUDA(dout); CHECK_CONTIG(dout); CHECK_CONTIG(out); CHECK_CONTIG(y);
+std::vector<Tensor> bn_elu_bwd(Tensor dout, c10::optional<Tensor> out, Tensor y, Tensor mean, Tensor invstd, Tensor gamma,
+                               c10::optional<Tensor> beta, c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta,
+                               bool want_dres, bool act) {
+  CHECK_F32_CUDA(dout); CHECK_CONTIG(dout); CHECK_CONTIG(y);
   c10::cuda::CUDAGuard guard(y.device());
   const int C = (int)y.size(-1);
   const int M = (int)(y.numel() / C);
+  const float* outp = nullptr;
+  if (out.has_value() && out->defined()) { CHECK_CONTIG((*out)); outp = out->data_ptr<float>(); }
+  const float* betap = opt_ptr(beta);
   auto sums = torch::empty({2 * C}, y.options());
-  fb::bn_elu_bwd_reduce(fptr(dout), fptr(out), fptr(y), fptr(mean), fptr(invstd), fptr_mut(sums), M, C, act ? 1 : 0, cur_stream());
+  fb::bn_elu_bwd_reduce(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums), M, C,
+                        act ? 1 : 0, cur_stream());
   auto dy = torch::empty_like(y);
   Tensor dres;
   if (want_dres) dres = torch::empty_like(y);
   float* dg = (dgamma.has_value() && dgamma->defined()) ? dgamma->data_ptr<float>() : nullptr;
   float* db = (dbeta.has_value() && dbeta->defined()) ? dbeta->data_ptr<float>() : nullptr;
-  fb::bn_elu_bwd_apply(fptr(dout), fptr(out), fptr(y), fptr(mean), fptr(invstd), fptr(gamma), fptr(sums), fptr_mut(dy),
+  fb::bn_elu_bwd_apply(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr(sums), fptr_mut(dy),
                        want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0, cur_stream());
   return {dy, dres};
 }

@@ -69,25 +69,90 @@ void normalize_u8_nhwc(const uint8_t* in, float* out, int npix, int c_out, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Thread layout for [M, C] tensors with C % 4 == 0: thread t handles channel quad (t % (C/4)) for rows
-// (t / (C/4)) + k * rows_per_iter.  Consecutive threads touch consecutive 16-B words of a row.
+// Thread layout for [M, C] tensors with C % 4 == 0 (q = C/4 channel quads): thread t owns quad (t % q) for the rows
+// (t / q) + k * rows_per_iter.  Consecutive threads touch consecutive 16-B words of a row, a thread's per-channel
+// parameters live in REGISTERS for the whole kernel (no per-element modulo, no shared-memory parameter reads), and
+// every loop keeps four independent 16-B loads per tensor in flight.
+//
+// Reductions end in atomicAdds on a [2C] vector that spans only a few 128-B lines, i.e. a few L2 slices: with ~600
+// blocks the ~10^5 same-line atomics, not the streaming, set the kernel time (col_stats measured 0.7 TB/s,
+// profiles/r1_run13_bn.log).  The reduction kernels therefore run at most two 512-thread blocks per SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int EW_THREADS = 256;
+constexpr int RED_THREADS = 512;
 
-__global__ void __launch_bounds__(EW_THREADS)
+struct RowLayout {
+  int q, cq, r0, rpi;
+};
+__device__ __forceinline__ RowLayout row_layout(int C, int threads) {
+  RowLayout L;
+  L.q = C >> 2;
+  if ((L.q & (L.q - 1)) == 0) {
+    const int sh = 31 - __clz(L.q);
+    L.cq = threadIdx.x & (L.q - 1);
+    L.r0 = threadIdx.x >> sh;
+    L.rpi = threads >> sh;
+  } else {
+    L.cq = threadIdx.x % L.q;
+    L.r0 = threadIdx.x / L.q;
+    L.rpi = threads / L.q;
+  }
+  return L;
+}
+__device__ __forceinline__ float4 ld4(const float* p, size_t row, int q, int cq) {
+  return reinterpret_cast<const float4*>(p)[row * q + cq];
+}
+__device__ __forceinline__ void st4(float* p, size_t row, int q, int cq, float4 v) {
+  reinterpret_cast<float4*>(p)[row * q + cq] = v;
+}
+// block-wide reduction of per-thread channel-quad partials (s1, s2) over the rows of the block, then one atomicAdd
+// per channel and block
+__device__ __forceinline__ void block_quad_reduce(const float (&s1)[4], const float (&s2)[4], float* sm, const RowLayout& L,
+                                                  float* out1, float* out2) {
+  const int T = blockDim.x;
+  float* a = sm + threadIdx.x * 4;
+  float* b = sm + T * 4 + threadIdx.x * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { a[j] = s1[j]; b[j] = s2[j]; }
+  __syncthreads();
+  // threads [0, 2q): the first q sum s1 of their quad over the block's rows, the next q sum s2
+  if (threadIdx.x < 2 * L.q) {
+    const int which = threadIdx.x >= L.q;
+    const int quad = threadIdx.x - which * L.q;
+    const float* base = sm + which * T * 4 + quad * 4;
+    float t[4] = {0, 0, 0, 0};
+    for (int rr = 0; rr < L.rpi; ++rr) {
+      const float4 v = *reinterpret_cast<const float4*>(base + rr * L.q * 4);
+      t[0] += v.x; t[1] += v.y; t[2] += v.z; t[3] += v.w;
+    }
+    float* dst = (which ? out2 : out1) + quad * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(dst + j, t[j]);
+  }
+}
+static int reduce_grid(int M, int rpi) {
+  int grid = (M + rpi * 4 - 1) / (rpi * 4);
+  if (grid > sm_count() * 2) grid = sm_count() * 2;
+  return grid < 1 ? 1 : grid;
+}
+static int stream_grid(int M, int rpi) {
+  int grid = (M + rpi * 4 - 1) / (rpi * 4);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  return grid < 1 ? 1 : grid;
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
 col_stats_kernel(const float* __restrict__ y, float* __restrict__ stats, int M, int C) {
-  extern __shared__ float sm[];                   // [2][EW_THREADS][4]
-  const int q = C >> 2;
-  const int cq = threadIdx.x % q, r0 = threadIdx.x / q, rpi = EW_THREADS / q;
+  extern __shared__ float sm[];                   // [2][RED_THREADS][4]
+  const RowLayout L = row_layout(C, RED_THREADS);
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  if (r0 < rpi) {
-    const int step = gridDim.x * rpi;
-    int r = blockIdx.x * rpi + r0;
-    // four independent 16-B loads in flight per thread (latency, not bandwidth, bounded the one-row-per-trip loop)
+  if (L.r0 < L.rpi) {
+    const int step = gridDim.x * L.rpi;
+    int r = blockIdx.x * L.rpi + L.r0;
     for (; r + 3 * step < M; r += 4 * step) {
       float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = reinterpret_cast<const float4*>(y + size_t(r + u * step) * C)[cq];
+      for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step), L.q, L.cq);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         s1[0] += v[u].x; s1[1] += v[u].y; s1[2] += v[u].z; s1[3] += v[u].w;
@@ -96,38 +161,17 @@ col_stats_kernel(const float* __restrict__ y, float* __restrict__ stats, int M, 
       }
     }
     for (; r < M; r += step) {
-      const float4 v = reinterpret_cast<const float4*>(y + size_t(r) * C)[cq];
+      const float4 v = ld4(y, size_t(r), L.q, L.cq);
       s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
       s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]); s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
     }
   }
-  float* a = sm + threadIdx.x * 4;
-  float* b = sm + EW_THREADS * 4 + threadIdx.x * 4;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { a[j] = s1[j]; b[j] = s2[j]; }
-  __syncthreads();
-  if (threadIdx.x < q) {
-    float t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
-    for (int rr = 0; rr < rpi; ++rr) {
-      const float* pa = sm + (rr * q + threadIdx.x) * 4;
-      const float* pb = sm + EW_THREADS * 4 + (rr * q + threadIdx.x) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { t1[j] += pa[j]; t2[j] += pb[j]; }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(stats + threadIdx.x * 4 + j, t1[j]);
-      atomicAdd(stats + C + threadIdx.x * 4 + j, t2[j]);
-    }
-  }
+  block_quad_reduce(s1, s2, sm, L, stats, stats + C);
 }
 void col_stats(const float* y, float* stats, int M, int C, cudaStream_t s) {
-  if ((C & 3) || C > 4 * EW_THREADS) throw std::runtime_error("fedb200: col_stats needs C % 4 == 0 and C <= 1024");
-  const int rpi = EW_THREADS / (C >> 2);
-  int grid = (M + rpi * 8 - 1) / (rpi * 8);
-  if (grid > sm_count() * 4) grid = sm_count() * 4;
-  if (grid < 1) grid = 1;
-  col_stats_kernel<<<grid, EW_THREADS, 2 * EW_THREADS * 4 * sizeof(float), s>>>(y, stats, M, C);
+  if ((C & 3) || C > 2 * RED_THREADS) throw std::runtime_error("fedb200: col_stats needs C % 4 == 0 and C <= 1024");
+  const int rpi = RED_THREADS / (C >> 2);
+  col_stats_kernel<<<reduce_grid(M, rpi), RED_THREADS, 2 * RED_THREADS * 4 * sizeof(float), s>>>(y, stats, M, C);
   check_launch("col_stats");
 }
 
@@ -136,33 +180,42 @@ bn_elu_fwd_kernel(const float* __restrict__ y, float* __restrict__ stats, const 
                   const float* __restrict__ beta, const float* __restrict__ residual, float* __restrict__ out,
                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
                   float* __restrict__ save_invstd, int M, int C, float eps, float momentum, int act, int self_clean) {
-  extern __shared__ float sm[];                   // scale[C] | shift[C]
   __shared__ int last_block;
-  float* scale = sm;
-  float* shift = sm + C;
-  const float invM = 1.f / float(M);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mean = stats[c] * invM;
-    float var = fmaf(-mean, mean, stats[C + c] * invM);
-    var = var > 0.f ? var : 0.f;
-    const float invstd = rsqrtf(var + eps);
-    const float sc = gamma[c] * invstd;
-    scale[c] = sc;
-    shift[c] = fmaf(-mean, sc, beta[c]);
-    if (blockIdx.x == 0) {
-      save_mean[c] = mean;
-      save_invstd[c] = invstd;
-      if (running_mean != nullptr) {
-        const float unbiased = M > 1 ? var * float(M) / float(M - 1) : var;
-        running_mean[c] = fmaf(momentum, mean - running_mean[c], running_mean[c]);
-        running_var[c] = fmaf(momentum, unbiased - running_var[c], running_var[c]);
+  const RowLayout L = row_layout(C, EW_THREADS);
+  const bool active = L.r0 < L.rpi;
+  float sc[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};
+  if (active) {
+    const float invM = 1.f / float(M);
+    const float4 s1 = reinterpret_cast<const float4*>(stats)[L.cq];
+    const float4 s2 = reinterpret_cast<const float4*>(stats + C)[L.cq];
+    const float4 g = reinterpret_cast<const float4*>(gamma)[L.cq];
+    const float4 b = reinterpret_cast<const float4*>(beta)[L.cq];
+    const float a1[4] = {s1.x, s1.y, s1.z, s1.w}, a2[4] = {s2.x, s2.y, s2.z, s2.w};
+    const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mean = a1[j] * invM;
+      float var = fmaf(-mean, mean, a2[j] * invM);
+      var = var > 0.f ? var : 0.f;
+      const float invstd = rsqrtf(var + eps);
+      sc[j] = gg[j] * invstd;
+      sh[j] = fmaf(-mean, sc[j], bb[j]);
+      if (blockIdx.x == 0 && L.r0 == 0) {
+        const int c = L.cq * 4 + j;
+        save_mean[c] = mean;
+        save_invstd[c] = invstd;
+        if (running_mean != nullptr) {
+          const float unbiased = M > 1 ? var * float(M) / float(M - 1) : var;
+          running_mean[c] = fmaf(momentum, mean - running_mean[c], running_mean[c]);
+          running_var[c] = fmaf(momentum, unbiased - running_var[c], running_var[c]);
+        }
       }
     }
   }
-  __syncthreads();
   if (self_clean) {
-    // Every block has now consumed the statistics.  The last one to say so zeroes the accumulators (and the counter
-    // behind them) for the next convolution that uses this buffer: no memset launch per layer, CUDA-graph safe.
+    // Every thread of this block has consumed the statistics.  The last block to say so zeroes the accumulators (and
+    // the counter behind them) for the next convolution that uses this buffer: no memset launch per layer.
+    __syncthreads();
     unsigned int* counter = reinterpret_cast<unsigned int*>(stats + 2 * C);
     if (threadIdx.x == 0) {
       __threadfence();
@@ -174,161 +227,207 @@ bn_elu_fwd_kernel(const float* __restrict__ y, float* __restrict__ stats, const 
       if (threadIdx.x == 0) *counter = 0u;
     }
   }
-  const int q = C >> 2;
-  const size_t total = size_t(M) * q;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int cq = int(i % q);
-    const float4 v = reinterpret_cast<const float4*>(y)[i];
-    const float4 sc = reinterpret_cast<const float4*>(scale)[cq];
-    const float4 sh = reinterpret_cast<const float4*>(shift)[cq];
-    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-    if (residual != nullptr) {
-      const float4 r = reinterpret_cast<const float4*>(residual)[i];
-      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-    }
+  if (!active) return;
+  const int step = gridDim.x * L.rpi;
+  auto apply = [&](float4 v, float4 r) {
+    float4 o = make_float4(fmaf(v.x, sc[0], sh[0]) + r.x, fmaf(v.y, sc[1], sh[1]) + r.y, fmaf(v.z, sc[2], sh[2]) + r.z,
+                           fmaf(v.w, sc[3], sh[3]) + r.w);
     if (act) { o.x = elu_f(o.x); o.y = elu_f(o.y); o.z = elu_f(o.z); o.w = elu_f(o.w); }
-    reinterpret_cast<float4*>(out)[i] = o;
+    return o;
+  };
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  int r = blockIdx.x * L.rpi + L.r0;
+  for (; r + 3 * step < M; r += 4 * step) {
+    float4 v[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step), L.q, L.cq);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rs[u] = residual != nullptr ? ld4(residual, size_t(r + u * step), L.q, L.cq) : zero;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st4(out, size_t(r + u * step), L.q, L.cq, apply(v[u], rs[u]));
+  }
+  for (; r < M; r += step) {
+    const float4 v = ld4(y, size_t(r), L.q, L.cq);
+    const float4 rs = residual != nullptr ? ld4(residual, size_t(r), L.q, L.cq) : zero;
+    st4(out, size_t(r), L.q, L.cq, apply(v, rs));
   }
 }
 void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* beta, const float* residual,
                 float* out, float* running_mean, float* running_var, float* save_mean, float* save_invstd, int M, int C,
                 float eps, float momentum, int act, int self_clean, cudaStream_t s) {
-  if (C & 3) throw std::runtime_error("fedb200: bn_elu_fwd needs C % 4 == 0");
-  const size_t total = size_t(M) * (C >> 2);
-  int grid = int((total + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
-  if (grid > sm_count() * 8) grid = sm_count() * 8;
-  if (grid < 1) grid = 1;
-  bn_elu_fwd_kernel<<<grid, EW_THREADS, 2 * C * sizeof(float), s>>>(y, stats, gamma, beta, residual, out, running_mean,
-                                                                    running_var, save_mean, save_invstd, M, C, eps,
-                                                                    momentum, act, self_clean);
+  if ((C & 3) || C > 4 * EW_THREADS) throw std::runtime_error("fedb200: bn_elu_fwd needs C % 4 == 0 and C <= 1024");
+  const int rpi = EW_THREADS / (C >> 2);
+  bn_elu_fwd_kernel<<<stream_grid(M, rpi), EW_THREADS, 0, s>>>(y, stats, gamma, beta, residual, out, running_mean,
+                                                                running_var, save_mean, save_invstd, M, C, eps, momentum,
+                                                                act, self_clean);
   check_launch("bn_elu_fwd");
 }
 
-// backward pass 1: sums[c] = sum_rows du, sums[C+c] = sum_rows du * xhat, with du = dout * ELU'(out)
-__global__ void __launch_bounds__(EW_THREADS)
+// du = dout * ELU'(z).  With the layer output at hand ELU' comes from it (z > 0 <=> out > 0, exp(z) = out + 1); when
+// the layer had no residual input, z = y * scale + shift is recomputed instead and `out` is never read (one tensor
+// pass less in each of the two backward kernels).
+struct BnBwdCoef {
+  float mu[4], is[4], sc[4], sh[4];
+};
+__device__ __forceinline__ BnBwdCoef bn_bwd_coef(const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                                 int cq) {
+  BnBwdCoef k;
+  const float4 m = reinterpret_cast<const float4*>(mean)[cq], i = reinterpret_cast<const float4*>(invstd)[cq];
+  const float4 g = reinterpret_cast<const float4*>(gamma)[cq];
+  const float4 b = beta != nullptr ? reinterpret_cast<const float4*>(beta)[cq] : make_float4(0.f, 0.f, 0.f, 0.f);
+  k.mu[0] = m.x; k.mu[1] = m.y; k.mu[2] = m.z; k.mu[3] = m.w;
+  k.is[0] = i.x; k.is[1] = i.y; k.is[2] = i.z; k.is[3] = i.w;
+  const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k.sc[j] = gg[j] * k.is[j];
+    k.sh[j] = fmaf(-k.mu[j], k.sc[j], bb[j]);
+  }
+  return k;
+}
+template <int MODE>   // 0: no activation, 1: ELU' from out, 2: ELU' recomputed from y
+__device__ __forceinline__ float4 bn_du(float4 d, float4 o, float4 v, const BnBwdCoef& k) {
+  if (MODE == 1) {
+    d.x *= elu_grad_from_out(o.x); d.y *= elu_grad_from_out(o.y); d.z *= elu_grad_from_out(o.z); d.w *= elu_grad_from_out(o.w);
+  } else if (MODE == 2) {
+    const float z0 = fmaf(v.x, k.sc[0], k.sh[0]), z1 = fmaf(v.y, k.sc[1], k.sh[1]);
+    const float z2 = fmaf(v.z, k.sc[2], k.sh[2]), z3 = fmaf(v.w, k.sc[3], k.sh[3]);
+    d.x *= z0 > 0.f ? 1.f : __expf(z0); d.y *= z1 > 0.f ? 1.f : __expf(z1);
+    d.z *= z2 > 0.f ? 1.f : __expf(z2); d.w *= z3 > 0.f ? 1.f : __expf(z3);
+  }
+  return d;
+}
+
+// backward pass 1: sums[c] = sum_rows du, sums[C+c] = sum_rows du * xhat
+template <int MODE>
+__global__ void __launch_bounds__(RED_THREADS)
 bn_elu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
-                         const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
-                         int M, int C, int act) {
+                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float* __restrict__ sums, int M, int C) {
   extern __shared__ float sm[];
-  const int q = C >> 2;
-  const int cq = threadIdx.x % q, r0 = threadIdx.x / q, rpi = EW_THREADS / q;
+  const RowLayout L = row_layout(C, RED_THREADS);
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  if (r0 < rpi) {
-    const float4 mu = reinterpret_cast<const float4*>(mean)[cq];
-    const float4 is = reinterpret_cast<const float4*>(invstd)[cq];
-    const int step = gridDim.x * rpi;
-    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
-    for (int r = blockIdx.x * rpi + r0; r < M; r += 2 * step) {
-      // two rows (six 16-B loads) in flight per thread
-      const bool two = r + step < M;
-      const size_t i0 = size_t(r) * q + cq, i1 = size_t(two ? r + step : r) * q + cq;
-      float4 d0 = reinterpret_cast<const float4*>(dout)[i0], d1 = reinterpret_cast<const float4*>(dout)[i1];
-      const float4 o0 = act ? reinterpret_cast<const float4*>(out)[i0] : one;
-      const float4 o1 = act ? reinterpret_cast<const float4*>(out)[i1] : one;
-      const float4 v0 = reinterpret_cast<const float4*>(y)[i0], v1 = reinterpret_cast<const float4*>(y)[i1];
-      if (act) {
-        d0.x *= elu_grad_from_out(o0.x); d0.y *= elu_grad_from_out(o0.y); d0.z *= elu_grad_from_out(o0.z); d0.w *= elu_grad_from_out(o0.w);
-        d1.x *= elu_grad_from_out(o1.x); d1.y *= elu_grad_from_out(o1.y); d1.z *= elu_grad_from_out(o1.z); d1.w *= elu_grad_from_out(o1.w);
-      }
-      if (!two) d1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      s1[0] += d0.x + d1.x; s1[1] += d0.y + d1.y; s1[2] += d0.z + d1.z; s1[3] += d0.w + d1.w;
-      s2[0] = fmaf(d0.x, (v0.x - mu.x) * is.x, fmaf(d1.x, (v1.x - mu.x) * is.x, s2[0]));
-      s2[1] = fmaf(d0.y, (v0.y - mu.y) * is.y, fmaf(d1.y, (v1.y - mu.y) * is.y, s2[1]));
-      s2[2] = fmaf(d0.z, (v0.z - mu.z) * is.z, fmaf(d1.z, (v1.z - mu.z) * is.z, s2[2]));
-      s2[3] = fmaf(d0.w, (v0.w - mu.w) * is.w, fmaf(d1.w, (v1.w - mu.w) * is.w, s2[3]));
+  if (L.r0 < L.rpi) {
+    const BnBwdCoef k = bn_bwd_coef(mean, invstd, gamma, beta, L.cq);
+    const int step = gridDim.x * L.rpi;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto acc = [&](float4 d, float4 v) {
+      s1[0] += d.x; s1[1] += d.y; s1[2] += d.z; s1[3] += d.w;
+      s2[0] = fmaf(d.x, (v.x - k.mu[0]) * k.is[0], s2[0]); s2[1] = fmaf(d.y, (v.y - k.mu[1]) * k.is[1], s2[1]);
+      s2[2] = fmaf(d.z, (v.z - k.mu[2]) * k.is[2], s2[2]); s2[3] = fmaf(d.w, (v.w - k.mu[3]) * k.is[3], s2[3]);
+    };
+    int r = blockIdx.x * L.rpi + L.r0;
+    for (; r + 3 * step < M; r += 4 * step) {
+      float4 d[4], o[4], v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[u] = ld4(dout, size_t(r + u * step), L.q, L.cq);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step), L.q, L.cq);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) o[u] = MODE == 1 ? ld4(out, size_t(r + u * step), L.q, L.cq) : zero;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc(bn_du<MODE>(d[u], o[u], v[u], k), v[u]);
+    }
+    for (; r < M; r += step) {
+      const float4 d = ld4(dout, size_t(r), L.q, L.cq), v = ld4(y, size_t(r), L.q, L.cq);
+      const float4 o = MODE == 1 ? ld4(out, size_t(r), L.q, L.cq) : zero;
+      acc(bn_du<MODE>(d, o, v, k), v);
     }
   }
-  float* a = sm + threadIdx.x * 4;
-  float* b = sm + EW_THREADS * 4 + threadIdx.x * 4;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { a[j] = s1[j]; b[j] = s2[j]; }
-  __syncthreads();
-  if (threadIdx.x < q) {
-    float t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
-    for (int rr = 0; rr < rpi; ++rr) {
-      const float* pa = sm + (rr * q + threadIdx.x) * 4;
-      const float* pb = sm + EW_THREADS * 4 + (rr * q + threadIdx.x) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { t1[j] += pa[j]; t2[j] += pb[j]; }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(sums + threadIdx.x * 4 + j, t1[j]);
-      atomicAdd(sums + C + threadIdx.x * 4 + j, t2[j]);
-    }
-  }
+  block_quad_reduce(s1, s2, sm, L, sums, sums + C);
+}
+static int bwd_mode(const float* out, const float* beta, int act) {
+  if (!act) return 0;
+  if (out != nullptr) return 1;
+  if (beta == nullptr) throw std::runtime_error("fedb200: bn_elu_bwd needs either the layer output or beta");
+  return 2;
 }
 void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                       float* sums, int M, int C, int act, cudaStream_t s) {
-  if ((C & 3) || C > 4 * EW_THREADS) throw std::runtime_error("fedb200: bn_elu_bwd needs C % 4 == 0 and C <= 1024");
+                       const float* gamma, const float* beta, float* sums, int M, int C, int act, cudaStream_t s) {
+  if ((C & 3) || C > 2 * RED_THREADS) throw std::runtime_error("fedb200: bn_elu_bwd needs C % 4 == 0 and C <= 1024");
   cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s);
-  const int rpi = EW_THREADS / (C >> 2);
-  int grid = (M + rpi * 8 - 1) / (rpi * 8);
-  if (grid > sm_count() * 4) grid = sm_count() * 4;
-  if (grid < 1) grid = 1;
-  bn_elu_bwd_reduce_kernel<<<grid, EW_THREADS, 2 * EW_THREADS * 4 * sizeof(float), s>>>(dout, out, y, mean, invstd, sums,
-                                                                                        M, C, act);
+  const int rpi = RED_THREADS / (C >> 2);
+  const int grid = reduce_grid(M, rpi);
+  const size_t smem = 2 * RED_THREADS * 4 * sizeof(float);
+  switch (bwd_mode(out, beta, act)) {
+    case 0: bn_elu_bwd_reduce_kernel<0><<<grid, RED_THREADS, smem, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
+    case 1: bn_elu_bwd_reduce_kernel<1><<<grid, RED_THREADS, smem, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
+    default: bn_elu_bwd_reduce_kernel<2><<<grid, RED_THREADS, smem, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
+  }
   check_launch("bn_elu_bwd_reduce");
 }
 
-// backward pass 2: dy = gamma*invstd*(du - sum_du/M - xhat*sum_du_xhat/M); dres = du; dgamma/dbeta from sums
+// backward pass 2: dy = gamma*invstd*(du - sum_du/M - xhat*sum_du_xhat/M); dres = du; dgamma/dbeta from sums.
+// Rows are visited from the END of the tensor: pass 1 has just streamed dout/y/out front to back, so their tails are
+// what the 126 MB L2 still holds.
+template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_elu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                        const float* __restrict__ gamma, const float* __restrict__ sums, float* __restrict__ dy,
-                        float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C,
-                        int act) {
-  extern __shared__ float sm[];                   // a[C] | b[C] | c[C] | mu[C]:  dy = a*du + b*y + c  (affine in du, y)
-  float* ca = sm;
-  float* cb = sm + C;
-  float* cc = sm + 2 * C;
-  const float invM = 1.f / float(M);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float g = gamma[c], is = invstd[c], mu = mean[c];
-    const float sdu = sums[c], sdx = sums[C + c];
-    // dy = g*is*(du - sdu/M - (y-mu)*is*sdx/M)
-    const float k = g * is;
-    ca[c] = k;
-    cb[c] = -k * is * sdx * invM;
-    cc[c] = -k * sdu * invM + k * is * sdx * invM * mu;
-    if (blockIdx.x == 0) {
-      if (dgamma != nullptr) dgamma[c] += sdx;
-      if (dbeta != nullptr) dbeta[c] += sdu;
+                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums,
+                        float* __restrict__ dy, float* __restrict__ dres, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int M, int C) {
+  const RowLayout L = row_layout(C, EW_THREADS);
+  if (L.r0 >= L.rpi) return;
+  const BnBwdCoef k = bn_bwd_coef(mean, invstd, gamma, beta, L.cq);
+  float ca[4], cb[4], cc[4];                      // dy = ca*du + cb*y + cc  (affine in du, y)
+  {
+    const float invM = 1.f / float(M);
+    const float4 a = reinterpret_cast<const float4*>(sums)[L.cq], b = reinterpret_cast<const float4*>(sums + C)[L.cq];
+    const float4 g = reinterpret_cast<const float4*>(gamma)[L.cq];
+    const float sdu[4] = {a.x, a.y, a.z, a.w}, sdx[4] = {b.x, b.y, b.z, b.w}, gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float kk = gg[j] * k.is[j];
+      ca[j] = kk;
+      cb[j] = -kk * k.is[j] * sdx[j] * invM;
+      cc[j] = -kk * sdu[j] * invM + kk * k.is[j] * sdx[j] * invM * k.mu[j];
+      if (blockIdx.x == 0 && L.r0 == 0) {
+        if (dgamma != nullptr) dgamma[L.cq * 4 + j] += sdx[j];
+        if (dbeta != nullptr) dbeta[L.cq * 4 + j] += sdu[j];
+      }
     }
   }
-  __syncthreads();
-  const int q = C >> 2;
-  const size_t total = size_t(M) * q;
-  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int cq = int(i % q);
-    float4 d = reinterpret_cast<const float4*>(dout)[i];
-    if (act) {
-      const float4 o = reinterpret_cast<const float4*>(out)[i];
-      d.x *= elu_grad_from_out(o.x); d.y *= elu_grad_from_out(o.y); d.z *= elu_grad_from_out(o.z); d.w *= elu_grad_from_out(o.w);
-    }
-    const float4 v = reinterpret_cast<const float4*>(y)[i];
-    const float4 a = reinterpret_cast<const float4*>(ca)[cq];
-    const float4 b = reinterpret_cast<const float4*>(cb)[cq];
-    const float4 c = reinterpret_cast<const float4*>(cc)[cq];
-    float4 r = make_float4(fmaf(a.x, d.x, fmaf(b.x, v.x, c.x)), fmaf(a.y, d.y, fmaf(b.y, v.y, c.y)),
-                           fmaf(a.z, d.z, fmaf(b.z, v.z, c.z)), fmaf(a.w, d.w, fmaf(b.w, v.w, c.w)));
-    reinterpret_cast<float4*>(dy)[i] = r;
-    if (dres != nullptr) reinterpret_cast<float4*>(dres)[i] = d;
+  const int step = gridDim.x * L.rpi;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto emit = [&](size_t row, float4 d, float4 v) {
+    st4(dy, row, L.q, L.cq, make_float4(fmaf(ca[0], d.x, fmaf(cb[0], v.x, cc[0])), fmaf(ca[1], d.y, fmaf(cb[1], v.y, cc[1])),
+                                        fmaf(ca[2], d.z, fmaf(cb[2], v.z, cc[2])), fmaf(ca[3], d.w, fmaf(cb[3], v.w, cc[3]))));
+    if (dres != nullptr) st4(dres, row, L.q, L.cq, d);
+  };
+  int r = blockIdx.x * L.rpi + L.r0;
+  for (; r + 3 * step < M; r += 4 * step) {
+    float4 d[4], o[4], v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d[u] = ld4(dout, size_t(M - 1 - (r + u * step)), L.q, L.cq);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(M - 1 - (r + u * step)), L.q, L.cq);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) o[u] = MODE == 1 ? ld4(out, size_t(M - 1 - (r + u * step)), L.q, L.cq) : zero;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(size_t(M - 1 - (r + u * step)), bn_du<MODE>(d[u], o[u], v[u], k), v[u]);
+  }
+  for (; r < M; r += step) {
+    const size_t row = size_t(M - 1 - r);
+    const float4 d = ld4(dout, row, L.q, L.cq), v = ld4(y, row, L.q, L.cq);
+    const float4 o = MODE == 1 ? ld4(out, row, L.q, L.cq) : zero;
+    emit(row, bn_du<MODE>(d, o, v, k), v);
   }
 }
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                      const float* gamma, const float* sums, float* dy, float* dres, float* dgamma, float* dbeta, int M,
-                      int C, int act, cudaStream_t s) {
-  const size_t total = size_t(M) * (C >> 2);
-  int grid = int((total + EW_THREADS * 4 - 1) / (EW_THREADS * 4));
-  if (grid > sm_count() * 8) grid = sm_count() * 8;
-  if (grid < 1) grid = 1;
-  bn_elu_bwd_apply_kernel<<<grid, EW_THREADS, 3 * C * sizeof(float), s>>>(dout, out, y, mean, invstd, gamma, sums, dy,
-                                                                          dres, dgamma, dbeta, M, C, act);
+                      const float* gamma, const float* beta, const float* sums, float* dy, float* dres, float* dgamma,
+                      float* dbeta, int M, int C, int act, cudaStream_t s) {
+  if ((C & 3) || C > 4 * EW_THREADS) throw std::runtime_error("fedb200: bn_elu_bwd needs C % 4 == 0 and C <= 1024");
+  const int rpi = EW_THREADS / (C >> 2);
+  const int grid = stream_grid(M, rpi);
+  switch (bwd_mode(out, beta, act)) {
+    case 0: bn_elu_bwd_apply_kernel<0><<<grid, EW_THREADS, 0, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+    case 1: bn_elu_bwd_apply_kernel<1><<<grid, EW_THREADS, 0, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+    default: bn_elu_bwd_apply_kernel<2><<<grid, EW_THREADS, 0, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+  }
   check_launch("bn_elu_bwd_apply");
 }
 
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 avgpool_kernel(const float* __restrict__ x, float* __restrict__ out, int NB, int HW, int C) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over NB*C

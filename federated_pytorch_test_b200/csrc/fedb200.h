@@ -42,11 +42,12 @@ void col_stats(const float* y, float* stats, int M, int C, cudaStream_t s);
 void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* beta, const float* residual,
                 float* out, float* running_mean, float* running_var, float* save_mean, float* save_invstd, int M, int C,
                 float eps, float momentum, int act, int self_clean, cudaStream_t s);
+// out == nullptr (allowed when the layer had no residual input): ELU' is recomputed from y, gamma, beta
 void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                       float* sums, int M, int C, int act, cudaStream_t s);
+                       const float* gamma, const float* beta, float* sums, int M, int C, int act, cudaStream_t s);
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                      const float* gamma, const float* sums, float* dy, float* dres, float* dgamma, float* dbeta, int M,
-                      int C, int act, cudaStream_t s);
+                      const float* gamma, const float* beta, const float* sums, float* dy, float* dres, float* dgamma,
+                      float* dbeta, int M, int C, int act, cudaStream_t s);
 void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_t s);
 void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaStream_t s);
 void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, int kw, cudaStream_t s);

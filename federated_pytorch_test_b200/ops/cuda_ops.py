@@ -207,20 +207,22 @@ class _ConvBnAct(torch.autograd.Function):
         y = e.conv2d_nhwc(xn, wk, stats, stride, pad, 1)
         res = _nhwc(residual) if residual is not None else None
         out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, res, running_mean, running_var, eps, momentum, act, self_clean)
-        ctx.save_for_backward(xn, wk, y, out, mean, invstd, gamma)
+        ctx.save_for_backward(xn, wk, y, out, mean, invstd, gamma, beta)
         ctx.cfg = (stride, pad, act, residual is not None, tuple(weight.shape), x.shape[1])
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dout):
         e = ext()
-        xn, wk, y, out, mean, invstd, gamma = ctx.saved_tensors
+        xn, wk, y, out, mean, invstd, gamma, beta = ctx.saved_tensors
         stride, pad, act, has_res, wshape, cin_logical = ctx.cfg
         need_x, need_w, need_g, need_b, need_r = ctx.needs_input_grad[:5]
         dn = _nhwc(dout)
         dgamma = torch.zeros_like(gamma) if need_g else None
         dbeta = torch.zeros_like(gamma) if need_b else None
-        dy, dres = e.bn_elu_bwd(dn, out, y, mean, invstd, gamma, dgamma, dbeta, bool(has_res and need_r), act)
+        # without a residual input ELU' is recomputed from y (one tensor read less per backward pass)
+        dy, dres = e.bn_elu_bwd(dn, out if (has_res or not act) else None, y, mean, invstd, gamma, beta, dgamma, dbeta,
+                                bool(has_res and need_r), act)
         dx = dw = None
         kh, kw = wshape[2], wshape[3]
         if need_x:

@@ -195,7 +195,8 @@ def test_conv2d_nhwc_tcgen05(B, H, Ci, Co, k, s, p):
 
 
 # ------------------------------------------------------------------------------------------ BN + ELU
-@pytest.mark.parametrize("C,M,res,act", [(64, 4096, False, True), (128, 2048, True, True), (512, 256, True, False), (12, 777, False, True)])
+@pytest.mark.parametrize("C,M,res,act", [(64, 4096, False, True), (128, 2048, True, True), (512, 256, True, False), (12, 777, False, True),
+                                          (256, 8192, False, True), (64, 131072, True, True)])
 def test_bn_elu_forward_backward(C, M, res, act):
     e = cuda_ops.ext()
     g = torch.Generator(device=DEV).manual_seed(C + M)
@@ -223,8 +224,11 @@ def test_bn_elu_forward_backward(C, M, res, act):
     torch.testing.assert_close(rv, rv2, rtol=1e-4, atol=1e-5)
     o.backward(dout)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    dy, dres = e.bn_elu_bwd(dout, out, y, mean, invstd, gamma, dg, db, res, act)
+    dy, dres = e.bn_elu_bwd(dout, out, y, mean, invstd, gamma, beta, dg, db, res, act)
     torch.testing.assert_close(dy, yr.grad, rtol=2e-3, atol=2e-4)
+    if not res and act:   # ELU' recomputed from y instead of read from the layer output
+        dy2, _ = e.bn_elu_bwd(dout, None, y, mean, invstd, gamma, beta, None, None, False, act)
+        torch.testing.assert_close(dy2, yr.grad, rtol=2e-3, atol=2e-4)
     torch.testing.assert_close(dg, gr.grad, rtol=2e-3, atol=2e-2)
     torch.testing.assert_close(db, br.grad, rtol=2e-3, atol=2e-2)
     if res:
