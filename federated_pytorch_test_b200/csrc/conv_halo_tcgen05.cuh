@@ -99,7 +99,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int cb = 0; cb < p.cblocks; ++cb) {
         const int s = cb % STAGES;
         const uint32_t ph = (cb / STAGES) & 1;
@@ -126,7 +126,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t ph = (cb / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_base = smem_u32(tiles + s * S::STAGE_BYTES);
         const uint32_t b_base = a_base + A_SLOT_BYTES;
 #pragma unroll 1

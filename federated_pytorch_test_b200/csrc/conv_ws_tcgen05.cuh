@@ -64,6 +64,7 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int tstride = int(gridDim.x) / n_slices;
   const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tstride - 1) / tstride : 0;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -84,10 +85,11 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== producer: this slice's filters once, then one halo box per (tile, channel block) =========
-    if (lane == 0 && my_tiles > 0) {
+    if (elect_one() && my_tiles > 0) {
       mbar_arrive_expect_tx(w_full, uint32_t(p.cblocks * 9 * S::W_TILE));
       for (int cb = 0; cb < p.cblocks; ++cb)
         for (int t = 0; t < 9; ++t)
@@ -118,7 +120,7 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // roughly one dependent instruction every 5-10 cycles, and a 128x64x8 MMA only lasts 48 cycles: measured in
     // tools/probe_mma.cu), so the loop is kept free of divisions and descriptor rebuilds: all 36 MMAs of a
     // (tile, channel block) are unrolled and every descriptor is base + compile-time/loop-invariant offset.
-    if (lane == 0 && my_tiles > 0) {
+    if (elect_one() && my_tiles > 0) {
       mbar_wait(w_full, 0);
       uint32_t tap_off[9];                                   // (r * Wp + sx) pixel rows of 128 B, encoded >> 4
 #pragma unroll

@@ -125,13 +125,13 @@ __device__ __forceinline__ void block_quad_reduce(const float (&s1)[4], const fl
       const float4 v = *reinterpret_cast<const float4*>(base + rr * L.q * 4);
       t[0] += v.x; t[1] += v.y; t[2] += v.z; t[3] += v.w;
     }
+    // one 16-B vector reduction per channel quad (resolved at L2, no return value)
     float* dst = (which ? out2 : out1) + quad * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(dst + j, t[j]);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
   }
 }
 static int reduce_grid(int M, int rpi) {
-  int grid = (M + rpi * 4 - 1) / (rpi * 4);
+  int grid = (M + rpi * 16 - 1) / (rpi * 16);     // >= 16 rows per thread: few blocks => few same-line reductions
   if (grid > sm_count() * 2) grid = sm_count() * 2;
   return grid < 1 ? 1 : grid;
 }
@@ -143,27 +143,24 @@ static int stream_grid(int M, int rpi) {
 
 __global__ void __launch_bounds__(RED_THREADS)
 col_stats_kernel(const float* __restrict__ y, float* __restrict__ stats, int M, int C) {
+  pdl_prologue();
   extern __shared__ float sm[];                   // [2][RED_THREADS][4]
   const RowLayout L = row_layout(C, RED_THREADS);
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
   if (L.r0 < L.rpi) {
     const int step = gridDim.x * L.rpi;
-    int r = blockIdx.x * L.rpi + L.r0;
-    for (; r + 3 * step < M; r += 4 * step) {
+    // always four rows in flight; rows past the end re-read row r and are masked out
+    for (int r = blockIdx.x * L.rpi + L.r0; r < M; r += 4 * step) {
       float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step), L.q, L.cq);
+      for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step < M ? r + u * step : r), L.q, L.cq);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        if (r + u * step >= M) v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         s1[0] += v[u].x; s1[1] += v[u].y; s1[2] += v[u].z; s1[3] += v[u].w;
         s2[0] = fmaf(v[u].x, v[u].x, s2[0]); s2[1] = fmaf(v[u].y, v[u].y, s2[1]);
         s2[2] = fmaf(v[u].z, v[u].z, s2[2]); s2[3] = fmaf(v[u].w, v[u].w, s2[3]);
       }
-    }
-    for (; r < M; r += step) {
-      const float4 v = ld4(y, size_t(r), L.q, L.cq);
-      s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
-      s2[0] = fmaf(v.x, v.x, s2[0]); s2[1] = fmaf(v.y, v.y, s2[1]); s2[2] = fmaf(v.z, v.z, s2[2]); s2[3] = fmaf(v.w, v.w, s2[3]);
     }
   }
   block_quad_reduce(s1, s2, sm, L, stats, stats + C);
@@ -171,7 +168,7 @@ col_stats_kernel(const float* __restrict__ y, float* __restrict__ stats, int M, 
 void col_stats(const float* y, float* stats, int M, int C, cudaStream_t s) {
   if ((C & 3) || C > 2 * RED_THREADS) throw std::runtime_error("fedb200: col_stats needs C % 4 == 0 and C <= 1024");
   const int rpi = RED_THREADS / (C >> 2);
-  col_stats_kernel<<<reduce_grid(M, rpi), RED_THREADS, 2 * RED_THREADS * 4 * sizeof(float), s>>>(y, stats, M, C);
+  launch_pdl(col_stats_kernel, dim3(reduce_grid(M, rpi)), dim3(RED_THREADS), 2 * RED_THREADS * 4 * sizeof(float), s, y, stats, M, C);
   check_launch("col_stats");
 }
 
@@ -180,6 +177,7 @@ bn_elu_fwd_kernel(const float* __restrict__ y, float* __restrict__ stats, const 
                   const float* __restrict__ beta, const float* __restrict__ residual, float* __restrict__ out,
                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
                   float* __restrict__ save_invstd, int M, int C, float eps, float momentum, int act, int self_clean) {
+  pdl_prologue();
   __shared__ int last_block;
   const RowLayout L = row_layout(C, EW_THREADS);
   const bool active = L.r0 < L.rpi;
@@ -236,20 +234,18 @@ bn_elu_fwd_kernel(const float* __restrict__ y, float* __restrict__ stats, const 
     return o;
   };
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  int r = blockIdx.x * L.rpi + L.r0;
-  for (; r + 3 * step < M; r += 4 * step) {
+  for (int r = blockIdx.x * L.rpi + L.r0; r < M; r += 4 * step) {
     float4 v[4], rs[4];
+    size_t row[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step), L.q, L.cq);
+    for (int u = 0; u < 4; ++u) row[u] = size_t(r + u * step < M ? r + u * step : r);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) rs[u] = residual != nullptr ? ld4(residual, size_t(r + u * step), L.q, L.cq) : zero;
+    for (int u = 0; u < 4; ++u) v[u] = ld4(y, row[u], L.q, L.cq);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) st4(out, size_t(r + u * step), L.q, L.cq, apply(v[u], rs[u]));
-  }
-  for (; r < M; r += step) {
-    const float4 v = ld4(y, size_t(r), L.q, L.cq);
-    const float4 rs = residual != nullptr ? ld4(residual, size_t(r), L.q, L.cq) : zero;
-    st4(out, size_t(r), L.q, L.cq, apply(v, rs));
+    for (int u = 0; u < 4; ++u) rs[u] = residual != nullptr ? ld4(residual, row[u], L.q, L.cq) : zero;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * step < M) st4(out, row[u], L.q, L.cq, apply(v[u], rs[u]));
   }
 }
 void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* beta, const float* residual,
@@ -257,7 +253,7 @@ void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* b
                 float eps, float momentum, int act, int self_clean, cudaStream_t s) {
   if ((C & 3) || C > 4 * EW_THREADS) throw std::runtime_error("fedb200: bn_elu_fwd needs C % 4 == 0 and C <= 1024");
   const int rpi = EW_THREADS / (C >> 2);
-  bn_elu_fwd_kernel<<<stream_grid(M, rpi), EW_THREADS, 0, s>>>(y, stats, gamma, beta, residual, out, running_mean,
+  launch_pdl(bn_elu_fwd_kernel, dim3(stream_grid(M, rpi)), dim3(EW_THREADS), 0, s, y, stats, gamma, beta, residual, out, running_mean,
                                                                 running_var, save_mean, save_invstd, M, C, eps, momentum,
                                                                 act, self_clean);
   check_launch("bn_elu_fwd");
@@ -304,6 +300,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 bn_elu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                          const float* __restrict__ beta, float* __restrict__ sums, int M, int C) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const RowLayout L = row_layout(C, RED_THREADS);
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
@@ -316,22 +313,22 @@ bn_elu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
       s2[0] = fmaf(d.x, (v.x - k.mu[0]) * k.is[0], s2[0]); s2[1] = fmaf(d.y, (v.y - k.mu[1]) * k.is[1], s2[1]);
       s2[2] = fmaf(d.z, (v.z - k.mu[2]) * k.is[2], s2[2]); s2[3] = fmaf(d.w, (v.w - k.mu[3]) * k.is[3], s2[3]);
     };
-    int r = blockIdx.x * L.rpi + L.r0;
-    for (; r + 3 * step < M; r += 4 * step) {
+    for (int r = blockIdx.x * L.rpi + L.r0; r < M; r += 4 * step) {
       float4 d[4], o[4], v[4];
+      size_t row[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) d[u] = ld4(dout, size_t(r + u * step), L.q, L.cq);
+      for (int u = 0; u < 4; ++u) row[u] = size_t(r + u * step < M ? r + u * step : r);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(r + u * step), L.q, L.cq);
+      for (int u = 0; u < 4; ++u) d[u] = ld4(dout, row[u], L.q, L.cq);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) o[u] = MODE == 1 ? ld4(out, size_t(r + u * step), L.q, L.cq) : zero;
+      for (int u = 0; u < 4; ++u) v[u] = ld4(y, row[u], L.q, L.cq);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc(bn_du<MODE>(d[u], o[u], v[u], k), v[u]);
-    }
-    for (; r < M; r += step) {
-      const float4 d = ld4(dout, size_t(r), L.q, L.cq), v = ld4(y, size_t(r), L.q, L.cq);
-      const float4 o = MODE == 1 ? ld4(out, size_t(r), L.q, L.cq) : zero;
-      acc(bn_du<MODE>(d, o, v, k), v);
+      for (int u = 0; u < 4; ++u) o[u] = MODE == 1 ? ld4(out, row[u], L.q, L.cq) : zero;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * step >= M) d[u] = zero;                 // masked row: contributes nothing
+        acc(bn_du<MODE>(d[u], o[u], v[u], k), v[u]);
+      }
     }
   }
   block_quad_reduce(s1, s2, sm, L, sums, sums + C);
@@ -350,9 +347,9 @@ void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, cons
   const int grid = reduce_grid(M, rpi);
   const size_t smem = 2 * RED_THREADS * 4 * sizeof(float);
   switch (bwd_mode(out, beta, act)) {
-    case 0: bn_elu_bwd_reduce_kernel<0><<<grid, RED_THREADS, smem, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
-    case 1: bn_elu_bwd_reduce_kernel<1><<<grid, RED_THREADS, smem, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
-    default: bn_elu_bwd_reduce_kernel<2><<<grid, RED_THREADS, smem, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
+    case 0: launch_pdl(bn_elu_bwd_reduce_kernel<0>, dim3(grid), dim3(RED_THREADS), smem, s, dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
+    case 1: launch_pdl(bn_elu_bwd_reduce_kernel<1>, dim3(grid), dim3(RED_THREADS), smem, s, dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
+    default: launch_pdl(bn_elu_bwd_reduce_kernel<2>, dim3(grid), dim3(RED_THREADS), smem, s, dout, out, y, mean, invstd, gamma, beta, sums, M, C); break;
   }
   check_launch("bn_elu_bwd_reduce");
 }
@@ -367,6 +364,7 @@ bn_elu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums,
                         float* __restrict__ dy, float* __restrict__ dres, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int M, int C) {
+  pdl_prologue();
   const RowLayout L = row_layout(C, EW_THREADS);
   if (L.r0 >= L.rpi) return;
   const BnBwdCoef k = bn_bwd_coef(mean, invstd, gamma, beta, L.cq);
@@ -395,23 +393,20 @@ bn_elu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                                         fmaf(ca[2], d.z, fmaf(cb[2], v.z, cc[2])), fmaf(ca[3], d.w, fmaf(cb[3], v.w, cc[3]))));
     if (dres != nullptr) st4(dres, row, L.q, L.cq, d);
   };
-  int r = blockIdx.x * L.rpi + L.r0;
-  for (; r + 3 * step < M; r += 4 * step) {
+  for (int r = blockIdx.x * L.rpi + L.r0; r < M; r += 4 * step) {
     float4 d[4], o[4], v[4];
+    size_t row[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) d[u] = ld4(dout, size_t(M - 1 - (r + u * step)), L.q, L.cq);
+    for (int u = 0; u < 4; ++u) row[u] = size_t(M - 1 - (r + u * step < M ? r + u * step : r));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4(y, size_t(M - 1 - (r + u * step)), L.q, L.cq);
+    for (int u = 0; u < 4; ++u) d[u] = ld4(dout, row[u], L.q, L.cq);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) o[u] = MODE == 1 ? ld4(out, size_t(M - 1 - (r + u * step)), L.q, L.cq) : zero;
+    for (int u = 0; u < 4; ++u) v[u] = ld4(y, row[u], L.q, L.cq);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) emit(size_t(M - 1 - (r + u * step)), bn_du<MODE>(d[u], o[u], v[u], k), v[u]);
-  }
-  for (; r < M; r += step) {
-    const size_t row = size_t(M - 1 - r);
-    const float4 d = ld4(dout, row, L.q, L.cq), v = ld4(y, row, L.q, L.cq);
-    const float4 o = MODE == 1 ? ld4(out, row, L.q, L.cq) : zero;
-    emit(row, bn_du<MODE>(d, o, v, k), v);
+    for (int u = 0; u < 4; ++u) o[u] = MODE == 1 ? ld4(out, row[u], L.q, L.cq) : zero;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (r + u * step < M) emit(row[u], bn_du<MODE>(d[u], o[u], v[u], k), v[u]);
   }
 }
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
@@ -421,15 +416,16 @@ void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const
   const int rpi = EW_THREADS / (C >> 2);
   const int grid = stream_grid(M, rpi);
   switch (bwd_mode(out, beta, act)) {
-    case 0: bn_elu_bwd_apply_kernel<0><<<grid, EW_THREADS, 0, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
-    case 1: bn_elu_bwd_apply_kernel<1><<<grid, EW_THREADS, 0, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
-    default: bn_elu_bwd_apply_kernel<2><<<grid, EW_THREADS, 0, s>>>(dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+    case 0: launch_pdl(bn_elu_bwd_apply_kernel<0>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+    case 1: launch_pdl(bn_elu_bwd_apply_kernel<1>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+    default: launch_pdl(bn_elu_bwd_apply_kernel<2>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
   }
   check_launch("bn_elu_bwd_apply");
 }
 
 __global__ void __launch_bounds__(256)
 avgpool_kernel(const float* __restrict__ x, float* __restrict__ out, int NB, int HW, int C) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over NB*C
   if (i >= NB * C) return;
   const int n = i / C, c = i - n * C;
@@ -439,11 +435,12 @@ avgpool_kernel(const float* __restrict__ x, float* __restrict__ out, int NB, int
   out[i] = s / float(HW);
 }
 void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_t s) {
-  avgpool_kernel<<<(NB * C + 255) / 256, 256, 0, s>>>(x, out, NB, HW, C);
+  launch_pdl(avgpool_kernel, dim3((NB * C + 255) / 256), dim3(256), 0, s, x, out, NB, HW, C);
   check_launch("avgpool_nhwc");
 }
 __global__ void __launch_bounds__(256)
 avgpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int NB, int HW, int C) {
+  pdl_prologue();
   const size_t total = size_t(NB) * HW * C;
   const float inv = 1.f / float(HW);
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -456,7 +453,7 @@ void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaS
   const size_t total = size_t(NB) * HW * C;
   int grid = int((total + 1023) / 1024);
   if (grid > sm_count() * 8) grid = sm_count() * 8;
-  avgpool_bwd_kernel<<<grid, 256, 0, s>>>(dout, dx, NB, HW, C);
+  launch_pdl(avgpool_bwd_kernel, dim3(grid), dim3(256), 0, s, dout, dx, NB, HW, C);
   check_launch("avgpool_nhwc_bwd");
 }
 
@@ -464,6 +461,7 @@ void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaS
 // (the stride-1 data gradient is a convolution of dY with these weights)
 __global__ void __launch_bounds__(256)
 weight_flip_kernel(const float* __restrict__ w, float* __restrict__ out, int C_out, int C_in, int kh, int kw) {
+  pdl_prologue();
   const int taps = kh * kw;
   const size_t total = size_t(C_out) * taps * C_in;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -477,7 +475,7 @@ void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, i
   const size_t total = size_t(C_out) * kh * kw * C_in;
   int grid = int((total + 255) / 256);
   if (grid > sm_count() * 8) grid = sm_count() * 8;
-  weight_flip_kernel<<<grid, 256, 0, s>>>(w, out, C_out, C_in, kh, kw);
+  launch_pdl(weight_flip_kernel, dim3(grid), dim3(256), 0, s, w, out, C_out, C_in, kh, kw);
   check_launch("weight_krsc_flip");
 }
 

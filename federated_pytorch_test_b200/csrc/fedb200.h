@@ -9,6 +9,37 @@ namespace fedb200 {
 void count_launch(int n = 1);
 long long launch_count();
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// A training step is ~200 short kernels (10-40 us each): launch latency + CTA ramp-up of kernel N+1 is hidden behind
+// the tail of kernel N by letting N+1 become resident early.  Every kernel launched through launch_pdl() executes
+// pdl_launch_dependents() first (lets ITS successor start scheduling) and pdl_wait() before its first global-memory
+// access (blocks until the predecessor grid has completed and flushed).  Opt-in with FEDB200_PDL=1: inside the
+// CUDA-graph step the launch gaps are already hidden and the measured step time did not change.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- tcgen05 implicit GEMM (gemm_tcgen05.cu) -------------------------------------------------------
 int pick_block_n(int M, int N);
 void linear_tf32(const float* x, const float* w, const float* bias, float* out, int M, int N, int K, int ldx, int ldw,

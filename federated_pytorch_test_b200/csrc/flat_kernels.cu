@@ -8,6 +8,8 @@
 // warp-shuffle -> shared -> one atomicAdd per block.
 #include "fedb200.h"
 
+#include <cstdlib>
+
 #include <cooperative_groups.h>
 #include <atomic>
 #include <stdexcept>
@@ -20,6 +22,14 @@ namespace fedb200 {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches.load(); }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("FEDB200_PDL");
+    v = (e != nullptr && std::atoi(e) != 0) ? 1 : 0;   // opt-in: measured neutral inside the captured step (2.93 vs 2.90 ms)
+  }
+  return v == 1;
+}
 
 static inline void check_launch(const char* name) {
   cudaError_t e = cudaGetLastError();

@@ -93,13 +93,15 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmPara
   cfg.blockDim = dim3(IG_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the kernel calls griddepcontrol.wait itself
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = CL;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = CL > 1 ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: igemm launch: ") + cudaGetErrorString(e));
   count_launch();
@@ -175,11 +177,14 @@ static bool use_pair_kernel(int M, int bn) {
 int pick_block_n(int M, int N) {
   const int forced = env_int("FEDB200_BLOCK_N", 0);
   if (forced == 32 || forced == 64 || forced == 128 || forced == 256) return forced;
-  (void)M;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
   if (N <= 128) return 128;
-  return 256;
+  // N >= 256: a 128x256 tile moves the fewest bytes per FLOP, but with few M tiles it leaves most SMs idle and forces
+  // split-K (memset + red.add epilogue + a separate statistics pass).  Measured (profiles/r1_run14_*): layer3-type
+  // convs run 28 us as 128 CTAs of 128x128 against 32 + 3.5 us as 2 x 64 split-K CTAs of 128x256.
+  const int m_tiles = (M + IG_BLOCK_M - 1) / IG_BLOCK_M;
+  return m_tiles * ((N + 255) / 256) >= 120 ? 256 : 128;
 }
 static int pick_cluster(int M) {
   // Measured (profiles/r1_run5_*, r1_run6_*): multicasting the weight tile across 2/4 CTAs does not change the
@@ -327,7 +332,7 @@ static void launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const HaloPa
   if (per_slice > tiles) per_slice = tiles;
   if (per_slice < 1) per_slice = 1;
   const int grid = per_slice * n_slices;
-  kernel<<<grid, IG_THREADS, S::TOTAL, stream>>>(ta, tb, p, tiles, n_slices);
+  launch_pdl(kernel, dim3(grid), dim3(IG_THREADS), S::TOTAL, stream, ta, tb, p, tiles, n_slices);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: ws conv launch: ") + cudaGetErrorString(e));
   count_launch();

@@ -19,6 +19,7 @@
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), one tmem_full mbarrier (MMA -> epilogue).
 #pragma once
 #include "sm100.cuh"
+#include "fedb200.h"
 
 namespace fedb200 {
 
@@ -94,6 +95,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int kb_count = min(p.kb_per_split, p.num_k_blocks - kb_begin);
   const int n_iters = (kb_count + KPS - 1) / KPS;                   // pipeline stages this CTA consumes
 
+  pdl_launch_dependents();              // the next kernel of the stream may start its own prologue now
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -112,10 +114,11 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                           // barriers/TMEM are set up; from here on global memory of earlier kernels is read
 
   if (warp == 0) {
     // ===================== TMA producer (one thread; no divisions inside the loop) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int img = 0, h0 = 0;
       if (p.is_conv) {
         img = m0 / p.HW_out;
@@ -166,7 +169,7 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BLOCK_N);
-    if (lane == 0) {
+    if (elect_one()) {
       const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(tiles));
       int s = 0;
       uint32_t ph = 0;
