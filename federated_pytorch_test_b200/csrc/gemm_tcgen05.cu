@@ -2,6 +2,7 @@
 // (Kernel: igemm_tcgen05.cuh.)  Torch-free translation unit: raw pointers + cudaStream_t.
 #include "fedb200.h"
 #include "igemm_tcgen05.cuh"
+#include "igemm_persist_tcgen05.cuh"
 #include "conv_halo_tcgen05.cuh"
 #include "igemm2_tcgen05.cuh"
 #include "conv_ws_tcgen05.cuh"
@@ -112,6 +113,39 @@ static int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
+// ---- persistent kernel (igemm_persist_tcgen05.cuh): default for cluster size 1 ----
+template <int BN, int ST, int KPS>
+static void launch_p(const CUtensorMap& ta, const CUtensorMap& tb, IgemmParams p, cudaStream_t stream) {
+  using S = IgemmPSmem<BN, ST, KPS>;
+  auto kernel = igemm_persistent_kernel<BN, ST, KPS>;
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(persistent): ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  p.m_tiles = (p.M + IG_BLOCK_M - 1) / IG_BLOCK_M;
+  p.n_tiles = (p.N + BN - 1) / BN;
+  p.total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(IG_THREADS), S::TOTAL, stream, ta, tb, p);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: persistent igemm launch: ") + cudaGetErrorString(e));
+  count_launch();
+}
+static void dispatch_p(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
+  switch (bn) {
+    case 32: launch_p<32, 4, 2>(ta, tb, p, s); break;
+    case 64: launch_p<64, 4, 2>(ta, tb, p, s); break;
+    case 128: launch_p<128, 3, 2>(ta, tb, p, s); break;
+    default: launch_p<256, 2, 2>(ta, tb, p, s); break;
+  }
+}
+
 // KPS = 1 keeps one k-block (4 MMAs) per barrier round trip (first version, kept for A/B runs: FEDB200_KPS=1) and is
 // what the cluster-multicast experiments use; KPS = 2 (default) halves the number of round trips.
 template <int BN, int ST1, int ST2>
@@ -123,6 +157,10 @@ static void dispatch_cl(int cl, const CUtensorMap& ta, const CUtensorMap& tb, co
 }
 
 static void dispatch(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t s) {
+  if (cl == 1 && env_int("FEDB200_KPS", 2) != 1 && env_int("FEDB200_PERSIST", 1) != 0) {
+    dispatch_p(bn, ta, tb, p, s);
+    return;
+  }
   switch (bn) {
     case 32: dispatch_cl<32, 8, 4>(cl, ta, tb, p, s); break;
     case 64: dispatch_cl<64, 6, 4>(cl, ta, tb, p, s); break;

@@ -1,0 +1,277 @@
+// Persistent variant of the implicit-GEMM kernel (igemm_tcgen05.cuh): one CTA per SM walks a static list of output
+// tiles (tile = blockIdx.x + i * gridDim.x over [K split][M tile][N tile]), the TMEM accumulator is double-buffered
+// and the epilogue of tile i runs under the MMAs of tile i + 1.
+//
+// Why: the one-tile-per-CTA kernel pays, per CTA, a prologue (barrier init, TMEM allocation, first TMA round trip:
+// ~1.5-2 us), an exposed epilogue (1-2 us) and a wave transition (~1.2 us).  Measured with every pipeline switched off
+// (tools/bench_ablate.py, profiles/r1_run12_ablation.log) that skeleton alone is 15 us of the 20 us a 1x1 shortcut
+// convolution takes (256 CTAs, 2 k-blocks each), and 20-25 us of every multi-wave layer.  Here the prologue is paid
+// once per SM and only the LAST tile's epilogue is exposed.
+//
+// Roles, pipelines and operand layouts are those of igemm_tf32_kernel (KPS k-blocks per smem stage, elect.sync-issued
+// TMA / tcgen05.mma); the smem ring simply keeps rolling across tiles.
+#pragma once
+#include "igemm_tcgen05.cuh"
+
+namespace fedb200 {
+
+template <int BLOCK_N, int STAGES, int KPS>
+struct IgemmPSmem {
+  using B = IgemmSmem<BLOCK_N, STAGES, KPS>;
+  static constexpr int A_BYTES = B::A_BYTES, B_BYTES = B::B_BYTES, KB_BYTES = B::KB_BYTES, STAGE_BYTES = B::STAGE_BYTES;
+  static constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;
+  static constexpr int PART_BYTES = 2 * 4 * BLOCK_N * 2 * 4;    // double-buffered by accumulator stage
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + SCRATCH_BYTES + PART_BYTES + BAR_BYTES + 1024;
+};
+
+struct TileCoord {
+  int m0, n0, kb_begin, kb_count;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, int block_n) {
+  const int n_idx = t % p.n_tiles;
+  const int rest = t / p.n_tiles;
+  const int m_idx = rest % p.m_tiles;
+  const int z = rest / p.m_tiles;
+  TileCoord c;
+  c.m0 = m_idx * IG_BLOCK_M;
+  c.n0 = n_idx * block_n;
+  c.kb_begin = z * p.kb_per_split;
+  c.kb_count = min(p.kb_per_split, p.num_k_blocks - c.kb_begin);
+  return c;
+}
+
+template <int BLOCK_N, int STAGES, int KPS>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const IgemmParams p) {
+  using S = IgemmPSmem<BLOCK_N, STAGES, KPS>;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N must be a multiple of 32 in [32,256]");
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES);
+  float* part = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::SCRATCH_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES + S::SCRATCH_BYTES + S::PART_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* t_full = empty_bar + STAGES;     // 2
+  uint64_t* t_empty = t_full + 2;            // 2
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t_full[s], 1);
+      mbar_init(&t_empty[s], 4);             // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord c = decode_tile(p, t, BLOCK_N);
+        int img = 0, h0 = 0;
+        if (p.is_conv) {
+          img = c.m0 / p.HW_out;
+          h0 = ((c.m0 - img * p.HW_out) / p.W_out) * p.stride - p.pad;
+        }
+        int tap = c.kb_begin / p.cblocks;
+        int cb = c.kb_begin - tap * p.cblocks;
+        int r = tap / p.taps_w, sx = tap - r * p.taps_w;
+        int left = c.kb_count, kb = c.kb_begin;
+        while (left > 0) {
+          const int nk = left < KPS ? left : KPS;
+          left -= nk;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* dst = tiles + s * S::STAGE_BYTES;
+          if (p.dbg & 1) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], uint32_t(nk * S::KB_BYTES));
+#pragma unroll
+            for (int j = 0; j < KPS; ++j) {
+              if (j < nk) {
+                uint8_t* a_dst = dst + j * S::KB_BYTES;
+                uint8_t* b_dst = a_dst + S::A_BYTES;
+                if (p.is_conv)
+                  tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad, h0 + r * p.dil, img);
+                else
+                  tma_load_2d(a_dst, &tmap_a, &full_bar[s], (kb + j) * IG_BLOCK_K, c.m0);
+                tma_load_2d(b_dst, &tmap_b, &full_bar[s], (r * p.taps_w + sx) * p.b_cols_per_tap + cb * IG_BLOCK_K, c.n0);
+                if (++cb == p.cblocks) {
+                  cb = 0;
+                  if (++sx == p.taps_w) { sx = 0; ++r; }
+                }
+              }
+            }
+          }
+          kb += nk;
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BLOCK_N);
+    if (elect_one()) {
+      const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(tiles));
+      int s = 0;
+      uint32_t ph = 0;
+      int j_tile = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j_tile) {
+        const TileCoord c = decode_tile(p, t, BLOCK_N);
+        const uint32_t acc = uint32_t(j_tile & 1);
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        mbar_wait(&t_empty[acc], ((j_tile >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        int left = c.kb_count;
+        bool first = true;
+        while (left > 0) {
+          const int nk = left < KPS ? left : KPS;
+          left -= nk;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t sd = desc0 + uint64_t(uint32_t(s) * uint32_t(S::STAGE_BYTES >> 4));
+          if (!(p.dbg & 2)) {
+#pragma unroll
+            for (int j = 0; j < KPS; ++j) {
+              if (j < nk) {
+                const uint64_t adesc = sd + uint64_t(j * (S::KB_BYTES >> 4));
+                const uint64_t bdesc = adesc + uint64_t(S::A_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+                  if (j == 0 && k == 0) umma_tf32(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+                  else umma_tf32_acc(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc);
+                }
+              }
+            }
+          }
+          first = false;
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&t_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    float* my_scratch = scratch + (warp - 2) * 32 * 33;
+    int j_tile = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j_tile) {
+      const TileCoord c = decode_tile(p, t, BLOCK_N);
+      const int acc = j_tile & 1;
+      const int row = c.m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* part_acc = part + acc * (4 * BLOCK_N * 2);
+      float* my_part = part_acc + (warp - 2) * BLOCK_N * 2;
+      mbar_wait(&t_full[acc], (j_tile >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N + c0), v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          const int col = c.n0 + c0 + j;
+          if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+          if (p.act) x = elu1(x);
+          f[j] = x;
+        }
+        if (row_ok && !(p.dbg & 4)) {
+          float* dst = p.out + size_t(row) * p.ldo + c.n0 + c0;
+          if (p.k_splits > 1) {
+            if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c.n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);
+            }
+          } else if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c.n0 + c0 + j < p.N) dst[j] = f[j];
+          }
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = row_ok ? f[j] : 0.f;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float x = my_scratch[r * 33 + lane];
+            s1 += x;
+            s2 = fmaf(x, x, s2);
+          }
+          my_part[c0 + lane] = s1;
+          my_part[BLOCK_N + c0 + lane] = s2;
+          __syncwarp();
+        }
+      }
+      // every TMEM read of this warp for accumulator `acc` is complete: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (p.stats != nullptr) {
+        // `part` is double-buffered by acc: the next tile writes the other half, and this half is only rewritten two
+        // tiles later, after every thread has passed the next tile's bar.sync (i.e. finished reading it here)
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        const int tt = threadIdx.x - 64;
+        for (int cc = tt; cc < BLOCK_N; cc += 128) {
+          if (c.n0 + cc < p.N) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              s1 += part_acc[w * BLOCK_N * 2 + cc];
+              s2 += part_acc[w * BLOCK_N * 2 + BLOCK_N + cc];
+            }
+            atomicAdd(p.stats + c.n0 + cc, s1);
+            atomicAdd(p.stats + p.N + c.n0 + cc, s2);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace fedb200

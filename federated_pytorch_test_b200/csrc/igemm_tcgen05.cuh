@@ -45,6 +45,7 @@ struct IgemmParams {
   int kb_per_split;      // split-K: CTA z handles k-blocks [z*kb_per_split, ...) and red.adds into a zeroed output
   int k_splits;          // 1 = plain stores (+ fused stats); > 1 = reduction through L2 atomics, stats done by caller
   int dbg;               // profiling ablations (FEDB200_DBG, results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no stores
+  int m_tiles, n_tiles, total_tiles;   // persistent kernel: tile t -> (t % n_tiles, (t / n_tiles) % m_tiles, K split)
 };
 
 // KPS = k-blocks (of 32 fp32 = one 128-B swizzle row) per pipeline stage.  One producer/consumer barrier round trip
