@@ -176,6 +176,10 @@ Tensor linear_tf32(Tensor x, Tensor w, c10::optional<Tensor> bias, bool act) {
   fb::linear_tf32(fptr(x), fptr(w), opt_ptr(bias), fptr_mut(out), M, N, K, K, K, N, act ? 1 : 0, cur_stream());
   return out;
 }
+void set_conv_trace(c10::optional<Tensor> buf) {
+  fb::set_conv_trace((buf.has_value() && buf->defined()) ? reinterpret_cast<long long*>(buf->data_ptr<int64_t>()) : nullptr);
+}
+void probe_launch(int64_t kind, int64_t grid, int64_t smem_bytes) { fb::probe_launch((int)kind, (int)grid, (int)smem_bytes, cur_stream()); }
 bool conv_supported(int64_t H_out, int64_t W_out, int64_t C_in, int64_t stride) {
   return fb::conv_geometry_supported((int)H_out, (int)W_out, (int)C_in, (int)stride);
 }
@@ -302,6 +306,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("weight_flip", &weight_flip);
   m.def("linear_tf32", &linear_tf32);
   m.def("conv_supported", &conv_supported);
+  m.def("probe_launch", &probe_launch);
+  m.def("set_conv_trace", &set_conv_trace);
   m.def("conv2d_nhwc", &conv2d_nhwc);
   m.def("cross_entropy_fwd", &cross_entropy_fwd);
   m.def("cross_entropy_bwd", &cross_entropy_bwd);

@@ -48,6 +48,9 @@ bool conv_geometry_supported(int H_out, int W_out, int C_in, int stride);
 void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
                       int kh, int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream);
 
+void set_conv_trace(long long* buf);   // [16] clock64 stamps of CTA 0 of the next persistent conv launches (nullptr = off)
+void probe_launch(int kind, int grid, int smem_bytes, cudaStream_t stream);   // launch-floor probes (tools/)
+
 // ---- flat-vector kernels (flat_kernels.cu) ---------------------------------------------------------
 void adam_prox(float* x, const float* g, float* m, float* v, const int* step_dev, int n, float lr, float b1, float b2,
                float eps, const float* z, const float* y, float rho, float l1, float l2, cudaStream_t s);

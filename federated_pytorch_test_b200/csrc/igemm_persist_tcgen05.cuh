@@ -15,10 +15,17 @@
 
 namespace fedb200 {
 
-template <int BLOCK_N, int STAGES, int KPS>
+// MT = M sub-tiles (of 128 rows) per CTA tile.  The kernels are bound by the L2 -> SM fabric (~12 TB/s chip-wide,
+// profiles/ROOFLINE.md), so what counts is bytes per FLOP: with MT = 2 one weight k-block feeds two activation tiles
+// (256 x BLOCK_N outputs per CTA): 48 KB instead of 64 KB per k-block for 256 x 128 outputs.
+template <int BLOCK_N, int STAGES, int KPS, int MT>
 struct IgemmPSmem {
-  using B = IgemmSmem<BLOCK_N, STAGES, KPS>;
-  static constexpr int A_BYTES = B::A_BYTES, B_BYTES = B::B_BYTES, KB_BYTES = B::KB_BYTES, STAGE_BYTES = B::STAGE_BYTES;
+  static constexpr int A_TILE_BYTES = IG_BLOCK_M * IG_BLOCK_K * 4;   // 16 KB
+  static constexpr int A_BYTES = MT * A_TILE_BYTES;
+  static constexpr int B_BYTES = BLOCK_N * IG_BLOCK_K * 4;
+  static constexpr int KB_BYTES = A_BYTES + B_BYTES;                  // one k-block: [A0 | A1 | B]
+  static constexpr int STAGE_BYTES = KPS * KB_BYTES;
+  static constexpr int ACC_STAGES = (2 * MT * BLOCK_N <= 512) ? 2 : 1;
   static constexpr int SCRATCH_BYTES = 4 * 32 * 33 * 4;
   static constexpr int PART_BYTES = 2 * 4 * BLOCK_N * 2 * 4;    // double-buffered by accumulator stage
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -28,27 +35,29 @@ struct IgemmPSmem {
 struct TileCoord {
   int m0, n0, kb_begin, kb_count;
 };
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, int block_n) {
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, int block_n, int block_m) {
   const int n_idx = t % p.n_tiles;
   const int rest = t / p.n_tiles;
   const int m_idx = rest % p.m_tiles;
   const int z = rest / p.m_tiles;
   TileCoord c;
-  c.m0 = m_idx * IG_BLOCK_M;
+  c.m0 = m_idx * block_m;
   c.n0 = n_idx * block_n;
   c.kb_begin = z * p.kb_per_split;
   c.kb_count = min(p.kb_per_split, p.num_k_blocks - c.kb_begin);
   return c;
 }
 
-template <int BLOCK_N, int STAGES, int KPS>
+template <int BLOCK_N, int STAGES, int KPS, int MT>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const IgemmParams p) {
-  using S = IgemmPSmem<BLOCK_N, STAGES, KPS>;
+  using S = IgemmPSmem<BLOCK_N, STAGES, KPS, MT>;
+  constexpr int ACC = S::ACC_STAGES;
+  constexpr int TILE_M = MT * IG_BLOCK_M;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N must be a multiple of 32 in [32,256]");
   static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages
+  constexpr uint32_t TMEM_COLS = ACC * MT * BLOCK_N < 32 ? 32 : ACC * MT * BLOCK_N;   // power of two: 64..512
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -63,6 +72,9 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+#define FEDB200_STAMP(i) do { if (tr) p.trace[(i)] = clock64(); } while (0)
+  if (threadIdx.x == 0) FEDB200_STAMP(0);
 
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
@@ -87,6 +99,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
+  if (threadIdx.x == 0) FEDB200_STAMP(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -94,11 +107,16 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(p, t, BLOCK_N);
-        int img = 0, h0 = 0;
-        if (p.is_conv) {
-          img = c.m0 / p.HW_out;
-          h0 = ((c.m0 - img * p.HW_out) / p.W_out) * p.stride - p.pad;
+        const TileCoord c = decode_tile(p, t, BLOCK_N, TILE_M);
+        int img[MT], h0[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          img[mt] = 0; h0[mt] = 0;
+          if (p.is_conv) {
+            const int m = c.m0 + mt * IG_BLOCK_M;      // past the end: image index >= NB, the TMA unit zero-fills
+            img[mt] = m / p.HW_out;
+            h0[mt] = ((m - img[mt] * p.HW_out) / p.W_out) * p.stride - p.pad;
+          }
         }
         int tap = c.kb_begin / p.cblocks;
         int cb = c.kb_begin - tap * p.cblocks;
@@ -118,10 +136,15 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               if (j < nk) {
                 uint8_t* a_dst = dst + j * S::KB_BYTES;
                 uint8_t* b_dst = a_dst + S::A_BYTES;
-                if (p.is_conv)
-                  tma_load_4d(a_dst, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad, h0 + r * p.dil, img);
-                else
-                  tma_load_2d(a_dst, &tmap_a, &full_bar[s], (kb + j) * IG_BLOCK_K, c.m0);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  if (p.is_conv)
+                    tma_load_4d(a_dst + mt * S::A_TILE_BYTES, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad,
+                                h0[mt] + r * p.dil, img[mt]);
+                  else
+                    tma_load_2d(a_dst + mt * S::A_TILE_BYTES, &tmap_a, &full_bar[s], (kb + j) * IG_BLOCK_K,
+                                c.m0 + mt * IG_BLOCK_M);
+                }
                 tma_load_2d(b_dst, &tmap_b, &full_bar[s], (r * p.taps_w + sx) * p.b_cols_per_tap + cb * IG_BLOCK_K, c.n0);
                 if (++cb == p.cblocks) {
                   cb = 0;
@@ -133,6 +156,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           kb += nk;
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (t == int(blockIdx.x)) FEDB200_STAMP(2); else if (t == int(blockIdx.x + gridDim.x)) FEDB200_STAMP(3);
       }
     }
   } else if (warp == 1) {
@@ -144,10 +168,10 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       uint32_t ph = 0;
       int j_tile = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j_tile) {
-        const TileCoord c = decode_tile(p, t, BLOCK_N);
-        const uint32_t acc = uint32_t(j_tile & 1);
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        mbar_wait(&t_empty[acc], ((j_tile >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+        const TileCoord c = decode_tile(p, t, BLOCK_N, TILE_M);
+        const uint32_t acc = uint32_t(j_tile % ACC);
+        const uint32_t d_tmem = tmem_base + acc * (MT * BLOCK_N);
+        mbar_wait(&t_empty[acc], ((j_tile / ACC) & 1) ^ 1);     // the epilogue has drained this accumulator
         tc_fence_after();
         int left = c.kb_count;
         bool first = true;
@@ -156,6 +180,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           left -= nk;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (j_tile == 0 && first) FEDB200_STAMP(4);
           const uint64_t sd = desc0 + uint64_t(uint32_t(s) * uint32_t(S::STAGE_BYTES >> 4));
           if (!(p.dbg & 2)) {
 #pragma unroll
@@ -165,8 +190,12 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const uint64_t bdesc = adesc + uint64_t(S::A_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
-                  if (j == 0 && k == 0) umma_tf32(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
-                  else umma_tf32_acc(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc);
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint64_t ad = adesc + uint64_t(mt * (S::A_TILE_BYTES >> 4) + 2 * k);
+                    if (j == 0 && k == 0) umma_tf32(d_tmem + mt * BLOCK_N, ad, bdesc, idesc, first ? 0u : 1u);
+                    else umma_tf32_acc(d_tmem + mt * BLOCK_N, ad, bdesc + uint64_t(2 * k), idesc);
+                  }
                 }
               }
             }
@@ -176,6 +205,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&t_full[acc]);
+        if (j_tile == 0) FEDB200_STAMP(5); else if (j_tile == 1) FEDB200_STAMP(6);
       }
     }
   } else {
@@ -184,71 +214,89 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     float* my_scratch = scratch + (warp - 2) * 32 * 33;
     int j_tile = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j_tile) {
-      const TileCoord c = decode_tile(p, t, BLOCK_N);
-      const int acc = j_tile & 1;
-      const int row = c.m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* part_acc = part + acc * (4 * BLOCK_N * 2);
+      const TileCoord c = decode_tile(p, t, BLOCK_N, TILE_M);
+      const int acc = j_tile % ACC;
+      float* part_acc = part + (j_tile & 1) * (4 * BLOCK_N * 2);    // double-buffered column partials
       float* my_part = part_acc + (warp - 2) * BLOCK_N * 2;
-      mbar_wait(&t_full[acc], (j_tile >> 1) & 1);
+      mbar_wait(&t_full[acc], (j_tile / ACC) & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0) { if (j_tile == 0) FEDB200_STAMP(7); else if (j_tile == 1) FEDB200_STAMP(9); }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N + c0), v);
-        tmem_ld_wait();
-        float f[32];
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = c.m0 + mt * IG_BLOCK_M + q * 32 + lane;
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * (MT * BLOCK_N) + mt * BLOCK_N + c0), v);
+          tmem_ld_wait();
+          // Convolutions have neither bias nor activation here: the accumulator goes out as it is.  (With the per-element
+          // bias / bounds / ELU predicates compiled in unconditionally this loop cost ~2800 cycles per 32-column chunk, the
+          // whole epilogue 7 us per 128x128 tile: tools/trace_conv.py, profiles/r1_run17_trace.log.)
+          float f[32];
+          if (p.bias == nullptr && !p.act) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          const int col = c.n0 + c0 + j;
-          if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-          if (p.act) x = elu1(x);
-          f[j] = x;
-        }
-        if (row_ok && !(p.dbg & 4)) {
-          float* dst = p.out + size_t(row) * p.ldo + c.n0 + c0;
-          if (p.k_splits > 1) {
-            if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(v[j]);
+              const int col = c.n0 + c0 + j;
+              if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+              if (p.act) x = elu1(x);
+              f[j] = x;
+            }
+          }
+          if (row_ok && !(p.dbg & 4)) {
+            float* dst = p.out + size_t(row) * p.ldo + c.n0 + c0;
+            if (p.k_splits > 1) {
+              if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c.n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);
+              }
+            } else if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (c.n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);
+                if (c.n0 + c0 + j < p.N) dst[j] = f[j];
             }
-          } else if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c.n0 + c0 + j < p.N) dst[j] = f[j];
           }
-        }
-        if (p.stats != nullptr) {
+          if (p.stats != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = row_ok ? f[j] : 0.f;
-          __syncwarp();
-          float s1 = 0.f, s2 = 0.f;
+            for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = row_ok ? f[j] : 0.f;
+            __syncwarp();
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float x = my_scratch[r * 33 + lane];
-            s1 += x;
-            s2 = fmaf(x, x, s2);
+            for (int r = 0; r < 32; ++r) {
+              const float x = my_scratch[r * 33 + lane];
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+            if (mt == 0) {
+              my_part[c0 + lane] = s1;
+              my_part[BLOCK_N + c0 + lane] = s2;
+            } else {
+              my_part[c0 + lane] += s1;
+              my_part[BLOCK_N + c0 + lane] += s2;
+            }
+            __syncwarp();
           }
-          my_part[c0 + lane] = s1;
-          my_part[BLOCK_N + c0 + lane] = s2;
-          __syncwarp();
         }
       }
       // every TMEM read of this warp for accumulator `acc` is complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (warp == 2 && lane == 0) { if (j_tile == 0) FEDB200_STAMP(8); else if (j_tile == 1) FEDB200_STAMP(10); }
       if (p.stats != nullptr) {
-        // `part` is double-buffered by acc: the next tile writes the other half, and this half is only rewritten two
-        // tiles later, after every thread has passed the next tile's bar.sync (i.e. finished reading it here)
+        // `part` is double-buffered by tile parity: the next tile writes the other half, and this half is only rewritten
+        // two tiles later, after every thread has passed the next tile's bar.sync (i.e. finished reading it here)
         asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
         const int tt = threadIdx.x - 64;
         for (int cc = tt; cc < BLOCK_N; cc += 128) {
@@ -268,10 +316,12 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     tc_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0) FEDB200_STAMP(11);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#undef FEDB200_STAMP
 }
 
 }  // namespace fedb200

@@ -46,6 +46,7 @@ struct IgemmParams {
   int k_splits;          // 1 = plain stores (+ fused stats); > 1 = reduction through L2 atomics, stats done by caller
   int dbg;               // profiling ablations (FEDB200_DBG, results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no stores
   int m_tiles, n_tiles, total_tiles;   // persistent kernel: tile t -> (t % n_tiles, (t / n_tiles) % m_tiles, K split)
+  long long* trace;      // optional [16] clock64 stamps of CTA 0 (tools/trace_conv.py); nullptr in production
 };
 
 // KPS = k-blocks (of 32 fp32 = one 128-B swizzle row) per pipeline stage.  One producer/consumer barrier round trip
@@ -216,14 +217,22 @@ igemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
       tmem_ld_wait();
+      // Convolutions have neither bias nor activation here: the accumulator goes out as it is.  (With the per-element
+      // bias / bounds / ELU predicates compiled in unconditionally this loop cost ~2800 cycles per 32-column chunk, the
+      // whole epilogue 7 us per 128x128 tile: tools/trace_conv.py, profiles/r1_run17_trace.log.)
       float f[32];
+      if (p.bias == nullptr && !p.act) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        const int col = n0 + c0 + j;
-        if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
-        if (p.act) x = elu1(x);
-        f[j] = x;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]);
+          const int col = n0 + c0 + j;
+          if (p.bias != nullptr && col < p.N) x += __ldg(p.bias + col);
+          if (p.act) x = elu1(x);
+          f[j] = x;
+        }
       }
       if (row_ok && !(p.dbg & 4)) {
         float* dst = p.out + size_t(row) * p.ldo + n0 + c0;

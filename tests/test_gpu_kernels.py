@@ -395,6 +395,10 @@ VARIANT_ENVS = [
     dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_KPS="1"),      # one k-block per pipeline stage
     dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_PERSIST="0"),  # one tile per CTA (non-persistent)
     dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="2", FEDB200_BLOCK_N="64"), # persistent, several tiles per CTA, split-K
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_MT="2"),       # 256-row CTA tiles (two accumulators share B)
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_MT="1"),
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="2", FEDB200_MT="2", FEDB200_BLOCK_N="256"),  # single TMEM stage
+    dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_MT="2", FEDB200_BLOCK_N="64"),
     dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="4"),                       # split-K with red.global.add
     dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_CLUSTER="4"),  # weight-tile TMA multicast
     dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1", FEDB200_2CTA="1"),     # cta_group::2 pairs
@@ -407,7 +411,7 @@ VARIANT_ENVS = [
 @pytest.mark.parametrize("B,H,Ci,Co", [(5, 32, 64, 64), (3, 32, 4, 64), (6, 16, 128, 128), (16, 8, 256, 256), (20, 32, 64, 64)])
 def test_conv_kernel_variants(monkeypatch, env, B, H, Ci, Co):
     import os
-    for k in ("FEDB200_WS", "FEDB200_HALO", "FEDB200_SPLITK", "FEDB200_CLUSTER", "FEDB200_2CTA", "FEDB200_BLOCK_N", "FEDB200_KPS", "FEDB200_PERSIST"):
+    for k in ("FEDB200_WS", "FEDB200_HALO", "FEDB200_SPLITK", "FEDB200_CLUSTER", "FEDB200_2CTA", "FEDB200_BLOCK_N", "FEDB200_KPS", "FEDB200_PERSIST", "FEDB200_MT"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)

@@ -12,10 +12,7 @@ from federated_pytorch_test_b200.ops import cuda_ops  # noqa: E402
 
 MODES = [("full", 0), ("noTMA", 1), ("noMMA", 2), ("noST", 4), ("noTMA+noST", 5), ("noMMA+noST", 6), ("noTMA+noMMA", 3),
          ("empty", 7), ("aligned", 8)]
-PATHS = [("auto", dict(FEDB200_WS="1", FEDB200_HALO="1", FEDB200_SPLITK="-1")),
-         ("generic", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="0")),
-         ("generic bn64", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="0", FEDB200_BLOCK_N="64")),
-         ("generic bn128", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="0", FEDB200_BLOCK_N="128"))]
+PATHS = [("default", dict(FEDB200_WS="1", FEDB200_HALO="1", FEDB200_SPLITK="0", FEDB200_BLOCK_N="0"))]
 
 
 def main():
@@ -28,7 +25,6 @@ def main():
         x = torch.randn(B, H, H, Ci, device=dev)
         w = torch.randn(Co, k, k, Ci, device=dev) / (k * k * Ci) ** 0.5
         for pname, env in PATHS:
-            os.environ.update(FEDB200_BLOCK_N="0")
             os.environ.update(env)
             row = []
             for _, bits in MODES:

@@ -15,15 +15,15 @@ SHAPES = [  # name, B, H, Cin, Cout, k, stride, pad
     ("l4.0.c1", 128, 8, 256, 512, 3, 2, 1), ("layer4", 128, 4, 512, 512, 3, 1, 1), ("l2.sc", 128, 32, 64, 128, 1, 2, 0),
 ]
 BASE = dict(FEDB200_HALO="1", FEDB200_CLUSTER="1", FEDB200_BLOCK_N="0", FEDB200_2CTA="0", FEDB200_SPLITK="0", FEDB200_WS="1",
-            FEDB200_KPS="2", FEDB200_DBG="0", FEDB200_PERSIST="1")
+            FEDB200_KPS="2", FEDB200_DBG="0", FEDB200_PERSIST="1", FEDB200_MT="1", FEDB200_MT2_KPS="1")
 VARIANTS = [
     ("default", {}),
     ("generic persist", dict(FEDB200_WS="0", FEDB200_HALO="0")),
-    ("generic 1tile/cta", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_PERSIST="0")),
-    ("generic nosplit", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_SPLITK="1")),
+    ("generic mt1", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_MT="1")),
+    ("generic mt2", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_MT="2")),
+    ("generic mt2 2x96K", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_MT="2", FEDB200_MT2_KPS="2")),
+    ("generic 6x32K", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_KPS="3")),
     ("generic bn128", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_BLOCK_N="128")),
-    ("generic bn256", dict(FEDB200_WS="0", FEDB200_HALO="0", FEDB200_BLOCK_N="256")),
-    ("halo", dict(FEDB200_WS="0", FEDB200_HALO="2")),
 ]
 
 
