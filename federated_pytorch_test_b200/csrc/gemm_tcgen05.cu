@@ -62,6 +62,19 @@ static CUtensorMap make_tmap_2d(const float* ptr, uint64_t rows, uint64_t cols, 
   return m;
 }
 
+// Output map for bulk stores / reduce-adds: plain FLOAT32 elements (the operand maps may use the TF32 element type)
+static CUtensorMap make_tmap_out(float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  check_cu(encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+           "cuTensorMapEncodeTiled(out)");
+  return m;
+}
+
 // NHWC activation viewed as [C, W, H, N]; a box covers boxN x boxH x boxW output pixels (traversal stride = conv
 // stride) x 32 channels and lands in shared memory as a [128 pixels x 128 B] K-major swizzled tile.
 static CUtensorMap make_tmap_nhwc(const float* ptr, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t boxN,
@@ -136,8 +149,11 @@ static void launch_p(const CUtensorMap& ta, const CUtensorMap& tb, IgemmParams p
   p.n_tiles = (p.N + BN - 1) / BN;
   p.total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
   p.trace = g_conv_trace;
+  // output map: box = 32 columns x 32 rows (one epilogue chunk of one warp), 128B swizzle like the operand maps
+  p.tma_store = ((p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && env_int("FEDB200_TMA_STORE", 1) != 0) ? 1 : 0;
+  const CUtensorMap tc = p.tma_store ? make_tmap_out(p.out, p.M, p.N, p.ldo, 32) : ta;
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(IG_THREADS), S::TOTAL, stream, ta, tb, p);
+  cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(IG_THREADS), S::TOTAL, stream, ta, tb, tc, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: persistent igemm launch: ") + cudaGetErrorString(e));
   count_launch();
 }

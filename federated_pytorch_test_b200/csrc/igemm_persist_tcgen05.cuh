@@ -51,7 +51,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int t, in
 template <int BLOCK_N, int STAGES, int KPS, int MT>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const IgemmParams p) {
+                        const __grid_constant__ CUtensorMap tmap_c, const IgemmParams p) {
   using S = IgemmPSmem<BLOCK_N, STAGES, KPS, MT>;
   constexpr int ACC = S::ACC_STAGES;
   constexpr int TILE_M = MT * IG_BLOCK_M;
@@ -80,6 +80,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.tma_store) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -210,8 +211,13 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers -> 128B-swizzled staging tile in shared memory -> ONE bulk tensor store (or reduce-add for
+    // split-K) per 32x32 chunk and warp.  Direct register stores put 32 different rows into every STG: 4-6k cycles per
+    // 128x128 tile against ~1.2k for the TMEM reads (tools/trace_conv.py); the bulk store is asynchronous, writes
+    // whole 128-B lines and clips rows/columns outside the tensor by itself.
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    float* my_scratch = scratch + (warp - 2) * 32 * 33;
+    float* stage = scratch + (warp - 2) * 1024;   // [32 rows][32 floats], 1024-B aligned, chunk index XOR (row & 7)
+    const uint32_t sw = uint32_t(lane & 7);
     int j_tile = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j_tile) {
       const TileCoord c = decode_tile(p, t, BLOCK_N, TILE_M);
@@ -223,16 +229,14 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
       if (warp == 2 && lane == 0) { if (j_tile == 0) FEDB200_STAMP(7); else if (j_tile == 1) FEDB200_STAMP(9); }
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        const int row = c.m0 + mt * IG_BLOCK_M + q * 32 + lane;
+        const int row0 = c.m0 + mt * IG_BLOCK_M + q * 32;
+        const int row = row0 + lane;
         const bool row_ok = row < p.M;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * (MT * BLOCK_N) + mt * BLOCK_N + c0), v);
           tmem_ld_wait();
-          // Convolutions have neither bias nor activation here: the accumulator goes out as it is.  (With the per-element
-          // bias / bounds / ELU predicates compiled in unconditionally this loop cost ~2800 cycles per 32-column chunk, the
-          // whole epilogue 7 us per 128x128 tile: tools/trace_conv.py, profiles/r1_run17_trace.log.)
           float f[32];
           if (p.bias == nullptr && !p.act) {
 #pragma unroll
@@ -247,17 +251,35 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               f[j] = x;
             }
           }
-          if (row_ok && !(p.dbg & 4)) {
+          const bool staged = p.tma_store || p.stats != nullptr;
+          if (staged) {
+            if (p.tma_store) {
+              if (lane == 0) tma_store_wait_read();      // the previous chunk's store has drained the staging tile
+              __syncwarp();
+            }
+            if (!row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = 0.f;   // clipped by the store; must not reach the statistics
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(stage + lane * 32 + ((uint32_t(j) ^ sw) << 2)) =
+                  make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (p.tma_store) fence_proxy_async();
+            __syncwarp();
+            if (p.tma_store && lane == 0 && !(p.dbg & 4)) {
+              if (p.k_splits > 1) tma_reduce_add_2d(&tmap_c, stage, c.n0 + c0, row0);
+              else tma_store_2d(&tmap_c, stage, c.n0 + c0, row0);
+              tma_store_commit();
+            }
+          }
+          if (!p.tma_store && row_ok && !(p.dbg & 4)) {
+            // fallback for outputs whose row pitch is not a multiple of 16 B (e.g. 10-class logits)
             float* dst = p.out + size_t(row) * p.ldo + c.n0 + c0;
             if (p.k_splits > 1) {
-              if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (c.n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);
-              }
+              for (int j = 0; j < 32; ++j)
+                if (c.n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);
             } else if (c.n0 + c0 + 32 <= p.N && (p.ldo & 3) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -268,13 +290,12 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             }
           }
           if (p.stats != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) my_scratch[lane * 33 + j] = row_ok ? f[j] : 0.f;
-            __syncwarp();
+            // column sums over this warp's 32 rows, read straight from the staging tile (conflict-free: for a fixed
+            // row the 32 lanes read the 32 floats of that row in a permuted order)
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-              const float x = my_scratch[r * 33 + lane];
+              const float x = stage[r * 32 + (((uint32_t(lane) >> 2) ^ uint32_t(r & 7)) << 2) + (lane & 3)];
               s1 += x;
               s2 = fmaf(x, x, s2);
             }
@@ -313,6 +334,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read();   // shared memory must outlive the last bulk store's read
     tc_fence_before();
   }
   __syncthreads();
