@@ -198,6 +198,23 @@ Tensor conv2d_nhwc(Tensor x, Tensor w, c10::optional<Tensor> stats, int64_t stri
   return y;
 }
 
+// Same kernel with an explicit output size: the window is anchored at (-pad, -pad) and whatever sticks out on the
+// bottom/right is zero-filled by the TMA unit (used by the stride-2 data gradient: 2x2 taps, pad 0, out = in size).
+Tensor conv2d_nhwc_sized(Tensor x, Tensor w, c10::optional<Tensor> stats, int64_t stride, int64_t pad, int64_t dil,
+                         int64_t Ho, int64_t Wo) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.size(3) == w.size(3), "conv2d_nhwc: x [N,H,W,Ci], w [Co,kh,kw,Ci]");
+  TORCH_CHECK(Ho > 0 && Wo > 0, "conv2d_nhwc_sized: positive output size");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), Ci = (int)x.size(3);
+  const int Co = (int)w.size(0), kh = (int)w.size(1), kw = (int)w.size(2);
+  auto y = torch::empty({NB, Ho, Wo, Co}, x.options());
+  float* st = (stats.has_value() && stats->defined()) ? stats->data_ptr<float>() : nullptr;
+  fb::conv2d_nhwc_tf32(fptr(x), fptr(w), fptr_mut(y), st, NB, H, W, Ci, Co, kh, kw, (int)stride, (int)pad, (int)dil, (int)Ho,
+                       (int)Wo, cur_stream());
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------------- losses
 std::vector<Tensor> cross_entropy_fwd(Tensor logits, Tensor labels) {
   CHECK_F32_CUDA(logits); CHECK_CONTIG(logits);
@@ -309,6 +326,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("probe_launch", &probe_launch);
   m.def("set_conv_trace", &set_conv_trace);
   m.def("conv2d_nhwc", &conv2d_nhwc);
+  m.def("conv2d_nhwc_sized", &conv2d_nhwc_sized);
   m.def("cross_entropy_fwd", &cross_entropy_fwd);
   m.def("cross_entropy_bwd", &cross_entropy_bwd);
   m.def("vae_loss_fwd", &vae_loss_fwd);

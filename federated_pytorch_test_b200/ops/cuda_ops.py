@@ -28,6 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _ext
+from . import conv_math
 
 _EXT = None
 TF32_LINEAR = os.environ.get("FEDB200_TF32_LINEAR", "0") == "1"
@@ -173,6 +174,7 @@ def clear_caches() -> None:
     """Drop cached derived tensors (call after loading a checkpoint into existing parameters)."""
     _FLIP_CACHE.clear()
     _STATS_BUFFERS.clear()
+    _S2_CACHE.clear()
 
 
 def _flipped_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
@@ -189,6 +191,45 @@ def _flipped_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
         if not torch.cuda.is_current_stream_capturing():   # graph-pool memory must not escape its graph
             _FLIP_CACHE[key] = hit
     return hit
+
+
+S2_DGRAD = os.environ.get("FEDB200_S2_DGRAD", "1") != "0"
+_S2_CACHE = {}
+
+
+def _packed_s2_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
+    """Filter of the stride-1 convolution that computes a stride-2 data gradient (conv_math.py); cached for frozen
+    layers exactly like the rotated filters above."""
+    key = (wk.data_ptr(), tuple(wk.shape))
+    if trainable:
+        _S2_CACHE.pop(key, None)
+        return conv_math.pack_dgrad_s2_weight(wk)
+    hit = _S2_CACHE.get(key)
+    if hit is None:
+        hit = conv_math.pack_dgrad_s2_weight(wk)
+        if not torch.cuda.is_current_stream_capturing():
+            _S2_CACHE[key] = hit
+    return hit
+
+
+def _s2_dgrad_supported(e, xn: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, pad: int) -> bool:
+    H, W, Ci = xn.shape[1], xn.shape[2], xn.shape[3]
+    Ho, Wo, Co = dy.shape[1], dy.shape[2], dy.shape[3]
+    if not S2_DGRAD or kh != kw or (kh, pad) not in ((3, 1), (1, 0)):
+        return False
+    if H != 2 * Ho or W != 2 * Wo or Co % 4 or Ci % 4:
+        return False
+    return bool(e.conv_supported(Ho, Wo, Co, 1))
+
+
+def _s2_dgrad(e, dy: torch.Tensor, wk: torch.Tensor, trainable: bool) -> torch.Tensor:
+    """dx [N, 2Ho, 2Wo, Ci] of a stride-2 convolution: one stride-1 implicit GEMM over dy + a pixel shuffle."""
+    wp = _packed_s2_weight(wk, trainable)
+    if wk.shape[1] == 1:      # 1x1: only tap (0, 0) of the 2x2 window is populated -> run it as a 1x1 convolution
+        w1 = wp[:, 0:1, 0:1, :].contiguous()
+        return conv_math.dgrad_s2(dy, w1, lambda x, w: e.conv2d_nhwc(x, w, None, 1, 0, 1))
+    Ho, Wo = dy.shape[1], dy.shape[2]
+    return conv_math.dgrad_s2(dy, wp, lambda x, w: e.conv2d_nhwc_sized(x, w, None, 1, 0, 1, Ho, Wo))
 
 
 class _ConvBnAct(torch.autograd.Function):
@@ -230,6 +271,8 @@ class _ConvBnAct(torch.autograd.Function):
             if stride == 1 and e.conv_supported(xn.shape[1], xn.shape[2], wshape[0], 1) and Ci % 4 == 0:
                 # data gradient of a stride-1 conv = conv of dy with the 180-degree rotated, transposed filter
                 dxn = e.conv2d_nhwc(dy, _flipped_weight(wk, need_w), None, 1, kh - 1 - pad, 1)
+            elif stride == 2 and _s2_dgrad_supported(e, xn, dy, kh, kw, pad):
+                dxn = _s2_dgrad(e, dy, wk, need_w)
             else:
                 dxn = torch.ops.aten.convolution_backward(
                     dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,

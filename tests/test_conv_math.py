@@ -1,0 +1,28 @@
+"""CPU check of the stride-2 data-gradient decomposition (ops/conv_math.py) against autograd."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from federated_pytorch_test_b200.ops import conv_math
+
+
+@pytest.mark.parametrize("k,pad", [(3, 1), (1, 0)])
+@pytest.mark.parametrize("N,H,Ci,Co", [(2, 8, 4, 8), (3, 16, 8, 12), (1, 4, 16, 4)])
+def test_stride2_dgrad_equals_autograd(k, pad, N, H, Ci, Co):
+    g = torch.Generator().manual_seed(k * 100 + H + Ci)
+    x = torch.randn(N, Ci, H, H, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Co, Ci, k, k, generator=g, dtype=torch.float64)
+    y = F.conv2d(x, w, None, 2, pad)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    w_krsc = w.permute(0, 2, 3, 1).contiguous()
+    wp = conv_math.pack_dgrad_s2_weight(w_krsc)
+    assert wp.shape == (4 * Ci, 2, 2, Co)
+    dx = conv_math.dgrad_s2(dy.permute(0, 2, 3, 1).contiguous(), wp, conv_math.conv2x2_oracle)
+    torch.testing.assert_close(dx.permute(0, 3, 1, 2), dx_ref, rtol=1e-10, atol=1e-10)
+
+
+def test_packed_filter_has_nine_of_sixteen_taps():
+    w = torch.ones(5, 3, 3, 7)
+    wp = conv_math.pack_dgrad_s2_weight(w)
+    assert int((wp != 0).sum()) == 9 * 5 * 7

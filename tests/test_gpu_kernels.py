@@ -194,6 +194,24 @@ def test_conv2d_nhwc_tcgen05(B, H, Ci, Co, k, s, p):
     torch.testing.assert_close(stats[Co:], (flat * flat).sum(0), rtol=5e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("B,H,Ci,Co,k,p", [(4, 32, 64, 128, 3, 1), (8, 16, 128, 256, 3, 1), (16, 8, 256, 512, 3, 1),
+                                         (4, 32, 64, 128, 1, 0), (16, 8, 256, 512, 1, 0)])
+def test_stride2_data_gradient_as_one_stride1_conv(B, H, Ci, Co, k, p):
+    """dgrad of the stride-2 sites = 2x2 stride-1 implicit GEMM over dy with the phase-packed filter + pixel shuffle."""
+    e = cuda_ops.ext()
+    g = torch.Generator(device=DEV).manual_seed(H + Ci + k)
+    x = torch.randn(B, H, H, Ci, device=DEV, generator=g)
+    w = torch.randn(Co, k, k, Ci, device=DEV, generator=g) / math.sqrt(k * k * Ci)
+    dy = torch.randn(B, H // 2, H // 2, Co, device=DEV, generator=g)
+    assert cuda_ops._s2_dgrad_supported(e, x, dy, k, k, p)
+    dx = cuda_ops._s2_dgrad(e, dy, w, True)
+    ref = torch.ops.aten.convolution_backward(
+        dy.permute(0, 3, 1, 2).double(), x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), None,
+        [2, 2], [p, p], [1, 1], False, [0, 0], 1, [True, False, False])[0].permute(0, 2, 3, 1).float()
+    assert dx.shape == ref.shape
+    assert rel_err(dx, ref) < 3e-3
+
+
 # ------------------------------------------------------------------------------------------ BN + ELU
 @pytest.mark.parametrize("C,M,res,act", [(64, 4096, False, True), (128, 2048, True, True), (512, 256, True, False), (12, 777, False, True),
                                           (256, 8192, False, True), (64, 131072, True, True)])
