@@ -48,9 +48,12 @@ def pack_dgrad_s2_weight(w_krsc: torch.Tensor) -> torch.Tensor:
     """``[Co, k, k, Ci]`` (k in {1, 3}) -> ``[4*Ci, 2, 2, Co]`` filter of the equivalent stride-1 convolution over dy."""
     Co, kh, kw, Ci = w_krsc.shape
     assert kh == kw and kh in (1, 3), "stride-2 phase decomposition implemented for 1x1/pad0 and 3x3/pad1"
-    taps = torch.cat([w_krsc.reshape(Co, kh * kw, Ci), w_krsc.new_zeros(Co, 1, Ci)], dim=1)       # + zero tap
-    idx = _tap_index_table(kh).to(w_krsc.device).reshape(-1)
-    sel = taps.index_select(1, idx).reshape(Co, 2, 2, 2, 2, Ci)                                   # co ph pw dr ds ci
+    # Pure device ops with Python-side indices: no index tensor is copied host -> device, so this is legal inside a
+    # CUDA-graph capture (the active block's filters are re-packed every step).
+    flat = w_krsc.reshape(Co, kh * kw, Ci)
+    zero = w_krsc.new_zeros(Co, Ci)
+    idx = _tap_index_table(kh).reshape(-1).tolist()
+    sel = torch.stack([flat[:, i] if i < kh * kw else zero for i in idx], dim=1).reshape(Co, 2, 2, 2, 2, Ci)   # co ph pw dr ds ci
     return sel.permute(1, 2, 5, 3, 4, 0).reshape(4 * Ci, 2, 2, Co).contiguous()
 
 
