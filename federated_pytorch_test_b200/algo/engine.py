@@ -134,6 +134,7 @@ class EngineConfig:
     max_minibatches: Optional[int] = None   # cap per round (benchmarks / smoke tests)
     aggregate_in_epoch_loop: bool = True    # reference: aggregation sits inside the epoch loop
     reset_optimizer_each_epoch: bool = False  # no_consensus_multi.py:129-132 recreates Adam every epoch (Q18)
+    nan_guard: str = "raise"         # non-finite aggregation residual: 'raise' | 'warn' | 'off' 
 
 
 class Engine:
@@ -289,6 +290,7 @@ class Engine:
         with self.timers.phase("aggregate"):
             metrics = self.strategy.aggregate(nadmm)
         ctx = {"nloop": nloop, "nadmm": nadmm, "epoch": epoch, "N": N, "rho_mean": self.strategy.rho_mean()}
+        self._check_finite(visit, metrics, ctx)
         if metrics:
             self.task.aggregate_log(visit, metrics, ctx, self)
             self.metrics.write(dict(kind="round", block=visit.ci, label=list(visit.label), model=visit.model, **ctx, **metrics))
@@ -297,6 +299,22 @@ class Engine:
                 acc = self.task.evaluate(self.replicas, self)
             if acc is not None:
                 self.metrics.write(dict(kind="eval", block=visit.ci, **ctx, accuracy=acc))
+
+    def _check_finite(self, visit: Visit, metrics: Optional[Dict[str, float]], ctx: Dict) -> None:
+        """Failure detection: the residuals are norms over the REDUCED vector of every worker, so one
+        NaN/Inf anywhere in any replica's block shows up here, one round after it appeared, on every rank."""
+        if not metrics or self.cfg.nan_guard == "off":
+            return
+        bad = [k for k in ("dual", "primal") if k in metrics and not math.isfinite(float(metrics[k]))]
+        if not bad:
+            return
+        msg = ("non-finite %s residual after aggregating block %s (ids %s) at loop %d, round %d, epoch %d on rank %d: "
+               "a replica diverged (NaN/Inf in its parameters, duals or consensus vector)"
+               % ("/".join(bad), visit.ci, list(visit.label), ctx["nloop"], ctx["nadmm"], ctx["epoch"], self.topo.rank))
+        self.metrics.write(dict(kind="fault", block=visit.ci, **ctx, nonfinite=bad))
+        if self.cfg.nan_guard == "raise":
+            raise FloatingPointError(msg)
+        self.log("WARNING: " + msg)
 
     # ------------------------------------------------------------------
     # CUDA-graphed Adam step

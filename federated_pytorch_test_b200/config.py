@@ -45,6 +45,7 @@ class CommonConfig:
     fix_shard_off_by_one: bool = False   # Q1
     intended_elastic_net_gate: bool = False  # Q2: regularise whenever the block holds dense-layer weights
     diagnostics: str = "post"       # Q17: 'post' (extra forward after the step) | 'pre'
+    nan_guard: str = "raise"        # non-finite aggregation residual: 'raise' | 'warn' | 'off'
     collective: str = "auto"        # 'auto' | 'fused' | 'torch'
     fast: bool = True               # use the hand-written sm_100a kernels on CUDA devices
     graphs: bool = True             # CUDA-graph the per-minibatch step when possible

@@ -39,6 +39,36 @@ def test_federated_multi_blocks_and_writeback():
     torch.testing.assert_close(a, b)
 
 
+def test_nan_in_one_replica_is_detected_at_the_next_aggregation():
+    """Failure detection: a diverged replica poisons the reduced vector; every rank sees a non-finite
+    residual at the next round and the engine stops with a message naming block and round (or warns)."""
+    from federated_pytorch_test_b200.algo.engine import Engine
+
+    def poison(e: Engine):
+        if e.steps_done == 1:
+            e.replicas[1].arenas["net"].data.fill_(float("nan"))
+
+    for guard in ("raise", "warn"):
+        lines = []
+        cfg = federated_multi.Config(**{**TINY, **dict(K=2, Nloop=1, Nadmm=1, max_minibatches=1, check_results=False,
+                                                       use_cuda=False, nan_guard=guard)})
+        orig_init = Engine.__init__
+
+        def patched(self, *a, **k):
+            orig_init(self, *a, **k)
+            self.step_hook = poison
+        Engine.__init__ = patched
+        try:
+            if guard == "raise":
+                with pytest.raises(FloatingPointError, match="non-finite dual residual after aggregating block"):
+                    federated_multi.run(cfg, log=lines.append)
+            else:
+                federated_multi.run(cfg, log=lines.append)
+                assert any(l.startswith("WARNING: non-finite dual residual") for l in lines)
+        finally:
+            Engine.__init__ = orig_init
+
+
 def test_fedprox_and_consensus_do_not_write_back():
     eng, lines = _run(fedprox_multi, K=2, Nloop=1, Nadmm=2, max_minibatches=2, check_results=False, use_cuda=False)
     assert lines[0].startswith("block=[4,5](48120,1.000000) ADMM=0/0 primal=")
