@@ -2,7 +2,9 @@
 classifier task, evaluation, legacy checkpoints.
 
 Reference call stack being re-implemented: SURVEY §3.1 (module-level script
-``federated_multi.py`` and siblings).
+``federated_multi.py`` and siblings): shard construction and per-worker normalisation
+``src/federated_multi.py:55-71``, model construction / identical initialisation ``:127-150``, evaluation with
+batch-statistics BatchNorm ``:108-121`` (Q4, Q5), end-of-run checkpoints ``:226-233`` and warm start ``:100-103``.
 """
 from __future__ import annotations
 

@@ -16,6 +16,11 @@ Kernel inventory (SURVEY §2.10 ids):
   G14-16 flat ops          adam_prox, penalty, L-BFGS algebra (see flatops.py)
   G22 normalize_u8         uint8 NHWC -> normalised float, layout change fused
 
+Reference call sites these replace (library calls in the reference): conv + BatchNorm + ELU + residual
+``src/simple_models.py:137-153`` / ``:191-216``, ``avg_pool2d`` + ``linear`` ``:213-216``, cross-entropy
+``src/federated_multi.py:132``, VAE loss ``src/federated_vae.py:96-108``, input normalisation
+``src/federated_multi.py:60-71``, Adam / penalty terms ``src/consensus_multi.py:214-220`` (see flatops.py).
+
 On a CUDA device a missing extension is an error, never a silent fall-back.
 """
 from __future__ import annotations

@@ -1,6 +1,11 @@
 """``FusedCollective`` — the block collectives as ONE sm_100a kernel each, reducing
 straight out of peer memory over NVLink (``csrc/comm_kernels.cu``).  No NCCL on this path.
 
+Reference loops being replaced (Python loops over a dict of K modules): FedAvg mean + write-back + dual residual
+``src/federated_multi.py:204-214``, FedProx mean + primal/dual residuals ``src/fedprox_multi.py:205-234``, ADMM z/y
+updates + residuals ``src/consensus_multi.py:226-299`` (Barzilai-Borwein dots ``:253-273`` go through
+``flatops.multi_dot``).
+
 Memory model: every replica's flat parameter arena (and, for
 ADMM, a same-shaped arena for the duals ``y``) is allocated from a
 :class:`SymmetricHeap`:

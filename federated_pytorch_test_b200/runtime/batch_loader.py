@@ -7,6 +7,9 @@ stream wait on it, and hands the slot back to the native threads once the copy
 has been consumed.  This is the ingress of the end-to-end path that ``bench.py``
 times (``h2d_bytes_per_step``).
 
+Reference equivalent: ``torch.utils.data.DataLoader`` over a ``SubsetRandomSampler``-less shard with CPU
+``transforms`` and a synchronous ``.to(mydevice)`` per minibatch (``src/federated_multi.py:60-71``, ``:172-175``).
+
 If the C++ extension cannot be built (no compiler) a pure-PyTorch gather with
 the same interface is used; it is functionally identical, just not overlapped.
 """

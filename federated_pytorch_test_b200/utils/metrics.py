@@ -1,7 +1,7 @@
 """Observability: CUDA-event phase timers (device time, max over ranks), JSONL
 metrics and the reference's print formats.
 
-The reference has ``import time`` and never calls it; its only outputs are the
+The reference has ``import time`` (``src/federated_multi.py:6``) and never calls it; its only outputs are the
 ``print`` lines whose exact formats are reproduced in :mod:`..utils.legacy_log`.
 """
 from __future__ import annotations
