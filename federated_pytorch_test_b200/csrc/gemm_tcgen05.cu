@@ -450,6 +450,12 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
   }
 }
 
+// Generic implicit-GEMM convolution.  bias / act (ELU) are applied in the epilogue (VAE / CPC convolutions, SURVEY G6;
+// no BatchNorm statistics and no split-K in that case).
+static void conv2d_generic(const float* x, const float* w, float* y, float* stats, const float* bias, int act, int NB, int H,
+                           int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
+                           cudaStream_t stream);
+
 void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
                       int kh, int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream) {
   if (ws_applicable(H, W, C_in, C_out, kh, kw, stride, pad, dil)) {
@@ -460,6 +466,18 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
     conv3x3_halo(x, w, y, stats, NB, H, W, C_in, C_out, stream);
     return;
   }
+  conv2d_generic(x, w, y, stats, nullptr, 0, NB, H, W, C_in, C_out, kh, kw, stride, pad, dil, H_out, W_out, stream);
+}
+
+void conv2d_nhwc_bias_act_tf32(const float* x, const float* w, const float* bias, int act, float* y, int NB, int H, int W,
+                               int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
+                               cudaStream_t stream) {
+  conv2d_generic(x, w, y, nullptr, bias, act, NB, H, W, C_in, C_out, kh, kw, stride, pad, dil, H_out, W_out, stream);
+}
+
+static void conv2d_generic(const float* x, const float* w, float* y, float* stats, const float* bias, int act, int NB, int H,
+                           int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
+                           cudaStream_t stream) {
   if (!conv_geometry_supported(H_out, W_out, C_in, stride))
     throw std::runtime_error("fedb200: conv geometry not supported by the tcgen05 path");
   const int rows = 128 / W_out;
@@ -480,13 +498,13 @@ void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, in
   p.taps_w = kw; p.b_cols_per_tap = C_in; p.is_conv = 1;
   p.HW_out = H_out * W_out; p.W_out = W_out;
   p.stride = stride; p.pad = pad; p.dil = dil;
-  p.out = y; p.ldo = C_out; p.bias = nullptr; p.act = 0; p.stats = stats;
+  p.out = y; p.ldo = C_out; p.bias = bias; p.act = act; p.stats = stats;
   p.k_splits = 1; p.kb_per_split = p.num_k_blocks; p.dbg = env_int("FEDB200_DBG", 0);
   // Split-K: the kernel is bound by what ONE SM can ingest (~40-60 B/cycle, profiles/r1_run8_*), so a grid that
   // leaves SMs idle (64 CTAs for layer3, 32 for layer4 with 128x256 tiles) wastes most of the chip.  Slice K until
   // ~one full wave of CTAs exists; partial tiles are reduced with red.global.add.v4 into a zeroed output and the
   // BatchNorm statistics come from a separate column pass (the outputs of these layers are only 4-8 MB).
-  if (!pair && cl == 1) {
+  if (!pair && cl == 1 && bias == nullptr && act == 0) {   // bias / activation must see the complete sum
     const int ctas = ((M + IG_BLOCK_M - 1) / IG_BLOCK_M) * ((C_out + bn - 1) / bn);
     int splits = env_int("FEDB200_SPLITK", 0);
     if (splits <= 0) {

@@ -295,6 +295,63 @@ class _ConvBnAct(torch.autograd.Function):
         return dx, dw, dgamma, dbeta, dr, None, None, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------
+# conv + bias (+ ELU) of the VAE / CPC networks: forward on the implicit-GEMM kernel, backward on ATen.
+# EXPERIMENTAL in this round (written after the GPU budget was spent: numerics not yet confirmed on a B200), therefore
+# opt-in: FEDB200_CONV_ACT=1.  tests/test_gpu_experimental.py holds the checks to run before flipping the default.
+# ----------------------------------------------------------------------------
+CONV_ACT = os.environ.get("FEDB200_CONV_ACT", "0") == "1"
+
+
+def conv_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
+    if not CONV_ACT or not isinstance(conv, nn.Conv2d) or isinstance(conv, nn.ConvTranspose2d):
+        return False
+    if x.dim() != 4 or x.dtype != torch.float32 or conv.groups != 1 or conv.padding_mode != "zeros":
+        return False
+    if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.dilation[0] != conv.dilation[1]:
+        return False
+    if isinstance(conv.padding, str) or conv.kernel_size[0] != conv.kernel_size[1]:
+        return False
+    k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+    H, W = x.shape[2], x.shape[3]
+    Ho, Wo = (H + 2 * p - d * (k - 1) - 1) // s + 1, (W + 2 * p - d * (k - 1) - 1) // s + 1
+    Ci, Co = conv.in_channels, conv.out_channels
+    if Ho < 1 or Wo < 1 or Co % 4 or not (Ci % 4 == 0 or Ci == 3):
+        return False
+    return bool(ext().conv_supported(Ho, Wo, Ci if Ci != 3 else 4, s))
+
+
+class _ConvAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, dil, act):
+        xn = _nhwc(x)
+        wk = _krsc(weight)
+        if xn.shape[3] == 3:   # 16-byte pixel pitch for the TMA box
+            xn = F.pad(xn, (0, 1))
+            wk = F.pad(wk, (0, 1))
+        out = ext().conv2d_nhwc_bias_act(xn, wk, bias, bool(act), stride, pad, dil)
+        ctx.save_for_backward(x, weight, out)
+        ctx.cfg = (stride, pad, dil, act, bias is not None)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, out = ctx.saved_tensors
+        stride, pad, dil, act, has_bias = ctx.cfg
+        d = _nhwc(dout)
+        if act:   # ELU'(z) from the output: z > 0 <=> out > 0, exp(z) = out + 1
+            d = d * torch.where(out > 0, torch.ones_like(out), out + 1.0)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and has_bias
+        dx, dw, db = torch.ops.aten.convolution_backward(
+            d.permute(0, 3, 1, 2), x, weight, [weight.shape[0]] if has_bias else None, [stride, stride], [pad, pad], [dil, dil],
+            False, [0, 0], 1, [bool(need_x), bool(need_w), bool(need_b)])
+        return (dx if need_x else None), (dw if need_w else None), (db if need_b else None), None, None, None, None
+
+
+def conv_act(x: torch.Tensor, conv: nn.Conv2d, act: bool = True) -> torch.Tensor:
+    return _ConvAct.apply(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], bool(act))
+
+
 def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, residual=None, act: bool = True) -> torch.Tensor:
     return _ConvBnAct.apply(x, conv.weight, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var,
                             conv.stride[0], conv.padding[0], bn.eps, bn.momentum, bool(act))

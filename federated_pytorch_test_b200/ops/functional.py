@@ -72,7 +72,14 @@ def pool_linear(x: torch.Tensor, linear: nn.Linear, window: int = 4) -> torch.Te
 
 
 def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor:
-    """``ELU?(conv(x))`` for the bias-carrying convs / transposed convs of the VAE and CPC nets."""
+    """``ELU?(conv(x))`` for the bias-carrying convs / transposed convs of the VAE and CPC nets
+    (/root/reference/src/simple_models.py:249-265, :441-451).  The tcgen05 path (conv + bias + ELU in one kernel) is
+    opt-in in this round (``FEDB200_CONV_ACT=1``, see cuda_ops.conv_act_supported)."""
+    if _use_fast(x):
+        from . import cuda_ops
+
+        if cuda_ops.conv_act_supported(x, conv):
+            return cuda_ops.conv_act(x, conv, act)
     y = conv(x)
     return F.elu(y) if act else y
 
