@@ -3,6 +3,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
+
 #include "fedb200.h"
 
 namespace fb = fedb200;
@@ -133,13 +135,18 @@ std::vector<Tensor> bn_elu_bwd(Tensor dout, c10::optional<Tensor> out, Tensor y,
   if (out.has_value() && out->defined()) { CHECK_CONTIG((*out)); outp = out->data_ptr<float>(); }
   const float* betap = opt_ptr(beta);
   auto sums = torch::empty({2 * C}, y.options());
-  fb::bn_elu_bwd_reduce(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums), M, C,
-                        act ? 1 : 0, cur_stream());
   auto dy = torch::empty_like(y);
   Tensor dres;
   if (want_dres) dres = torch::empty_like(y);
   float* dg = (dgamma.has_value() && dgamma->defined()) ? dgamma->data_ptr<float>() : nullptr;
   float* db = (dbeta.has_value() && dbeta->defined()) ? dbeta->data_ptr<float>() : nullptr;
+  static const bool fused_optin = [] { const char* e = std::getenv("FEDB200_BN_BWD_FUSED"); return e != nullptr && std::atoi(e) != 0; }();
+  if (fused_optin && fb::bn_elu_bwd_fused(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums),
+                                          fptr_mut(dy), want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0,
+                                          cur_stream()))
+    return {dy, dres};
+  fb::bn_elu_bwd_reduce(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums), M, C,
+                        act ? 1 : 0, cur_stream());
   fb::bn_elu_bwd_apply(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr(sums), fptr_mut(dy),
                        want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0, cur_stream());
   return {dy, dres};

@@ -86,6 +86,10 @@ void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, cons
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
                       const float* gamma, const float* beta, const float* sums, float* dy, float* dres, float* dgamma,
                       float* dbeta, int M, int C, int act, cudaStream_t s);
+// experimental single-kernel backward for small tensors (returns false when not applicable; sums: [2C] scratch)
+bool bn_elu_bwd_fused(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, float* sums, float* dy, float* dres, float* dgamma,
+                      float* dbeta, int M, int C, int act, cudaStream_t s);
 void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_t s);
 void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaStream_t s);
 void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, int kw, cudaStream_t s);

@@ -44,3 +44,32 @@ def test_conv_bias_act_forward_backward(B, H, Ci, Co, k, s, p, d, act):
     gx, gw, gb = torch.autograd.grad(y, (x, conv.weight, conv.bias), g)
     rx, rw, rb = torch.autograd.grad(ref, (x, conv.weight, conv.bias), g)
     assert rel_err(gx, rx) < 5e-3 and rel_err(gw, rw) < 5e-3 and rel_err(gb, rb) < 5e-3
+
+
+# run with FEDB200_BN_BWD_FUSED=1: the binding then takes the single-kernel path for tensors that fit in registers
+@pytest.mark.parametrize("C,M,res,act", [(256, 8192, False, True), (256, 8192, True, True), (512, 2048, True, True),
+                                         (512, 2048, False, False), (128, 1000, False, True)])
+def test_fused_bn_backward_equals_two_pass_oracle(C, M, res, act):
+    assert os.environ.get("FEDB200_BN_BWD_FUSED", "0") == "1", "set FEDB200_BN_BWD_FUSED=1 before importing the extension"
+    e = cuda_ops.ext()
+    g = torch.Generator(device=DEV).manual_seed(C + M)
+    y = torch.randn(M, C, device=DEV, generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(C, device=DEV, generator=g) + 0.5, torch.randn(C, device=DEV, generator=g)
+    r = torch.randn(M, C, device=DEV, generator=g) if res else None
+    dout = torch.randn(M, C, device=DEV, generator=g)
+    yr, gr, br = y.clone().requires_grad_(), gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    rr = r.clone().requires_grad_() if res else None
+    u = F.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5)
+    if res:
+        u = u + rr
+    o = F.elu(u) if act else u
+    o.backward(dout)
+    mean = y.mean(0)
+    invstd = torch.rsqrt(y.var(0, unbiased=False) + 1e-5)
+    dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    dy, dres = e.bn_elu_bwd(dout, o.detach() if (res or not act) else None, y, mean, invstd, gamma, beta, dg, db, res, act)
+    torch.testing.assert_close(dy, yr.grad, rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(dg, gr.grad, rtol=2e-3, atol=2e-2)
+    torch.testing.assert_close(db, br.grad, rtol=2e-3, atol=2e-2)
+    if res:
+        torch.testing.assert_close(dres, rr.grad, rtol=1e-4, atol=1e-5)
