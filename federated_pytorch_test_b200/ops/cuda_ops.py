@@ -308,9 +308,9 @@ def conv_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
         return False
     if x.dim() != 4 or x.dtype != torch.float32 or conv.groups != 1 or conv.padding_mode != "zeros":
         return False
-    if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.dilation[0] != conv.dilation[1]:
-        return False
     if isinstance(conv.padding, str) or conv.kernel_size[0] != conv.kernel_size[1]:
+        return False
+    if conv.stride[0] != conv.stride[1] or conv.padding[0] != conv.padding[1] or conv.dilation[0] != conv.dilation[1]:
         return False
     k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
     H, W = x.shape[2], x.shape[3]
