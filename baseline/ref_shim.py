@@ -141,7 +141,10 @@ def run_reference_bench(gpus: int, steps: int, warmup: int) -> Dict:
         return {"impl": "reference", "unavailable": "baseline/_ref missing: run baseline/install_reference.sh (copies /root/reference; it has no setup.py to pip-install)"}
     if not torch.cuda.is_available():
         return {"impl": "reference", "unavailable": "no CUDA device"}
-    consts = dict(K=gpus, Nloop=1000, Nadmm=3, Nepoch=1, use_resnet=True, check_results=False, save_model=False,
+    # same rule as the product arm (bench.py): block 0 stays active for the whole measurement
+    per_round = max(1, -(-(50000 // gpus - 1) // 128))
+    nadmm = max(3, -(-((warmup + steps) + 4) // per_round) + 1)
+    consts = dict(K=gpus, Nloop=1000, Nadmm=nadmm, Nepoch=1, use_resnet=True, check_results=False, save_model=False,
                   be_verbose=False, load_model=False)
     from bench import ClockSampler  # same clock sampling as the product arm
 
