@@ -57,7 +57,7 @@ def load_cifar(cfg: CommonConfig, device: torch.device) -> CifarData:
     if cfg.data == "torchvision":
         data = CifarData.from_torchvision()
     else:
-        data = CifarData.synthetic(cfg.data_seed, cfg.train_size, cfg.test_size)
+        data = CifarData.synthetic(cfg.data_seed, cfg.train_size, cfg.test_size, getattr(cfg, "data_noise", 0.6))
     if cfg.data_on_device or device.type != "cuda":
         return data.to(device)
     return data.to(device, pin=True)  # pinned host memory; batches go through the native assembler

@@ -39,6 +39,7 @@ class CommonConfig:
     seed: int = 69                  # torch.manual_seed(69) at the top of every reference script
     data: str = "synthetic"         # 'synthetic' | 'torchvision' (needs local files, never downloads)
     data_seed: int = 1234
+    data_noise: float = 0.6         # synthetic data: noise std relative to the class-template amplitude (harder when larger)
     train_size: int = 50000
     test_size: int = 10000
     data_on_device: bool = True     # dataset resident in HBM; False = pinned host + native batch assembler

@@ -131,9 +131,10 @@ class CifarData:
     test_labels: torch.Tensor
 
     @staticmethod
-    def synthetic(seed: int = 1234, train_size: Optional[int] = None, test_size: Optional[int] = None) -> "CifarData":
-        tr = make_synthetic_cifar(True, seed, train_size)
-        te = make_synthetic_cifar(False, seed, test_size)
+    def synthetic(seed: int = 1234, train_size: Optional[int] = None, test_size: Optional[int] = None,
+                  noise: float = 0.6) -> "CifarData":
+        tr = make_synthetic_cifar(True, seed, train_size, noise)
+        te = make_synthetic_cifar(False, seed, test_size, noise)
         return CifarData(tr[0], tr[1], te[0], te[1])
 
     @staticmethod

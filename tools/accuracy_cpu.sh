@@ -4,7 +4,8 @@
 # the absolute numbers are not comparable with the reference's comparison.png — the shape and the ordering are).
 cd "$(dirname "$0")/.."
 OUT=profiles/accuracy_cpu
-COMMON="--K 4 --no-use_cuda --train_size 8000 --test_size 2000 --no-save_model --check_results"
+# --data_noise 3.0: noise std = 3x the template amplitude, which puts the small Net in the 40-70 % range (CIFAR10-like difficulty)
+COMMON="--K 4 --no-use_cuda --train_size 16000 --test_size 2000 --data_noise 3.0 --no-save_model --check_results"
 export OMP_NUM_THREADS=8
 python federated_multi.py  $COMMON --Nloop 4 --metrics_path $OUT/fedavg.jsonl   > $OUT/fedavg.log 2>&1
 python fedprox_multi.py    $COMMON --Nloop 4 --metrics_path $OUT/fedprox.jsonl  > $OUT/fedprox.log 2>&1
