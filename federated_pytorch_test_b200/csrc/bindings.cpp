@@ -151,6 +151,25 @@ std::vector<Tensor> bn_elu_bwd(Tensor dout, c10::optional<Tensor> out, Tensor y,
                        want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0, cur_stream());
   return {dy, dres};
 }
+// fused classifier head (experimental): x [N,H,W,C], w [O,C], bias [O] -> (logits [N,O], pooled [N,C])
+std::vector<Tensor> head_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias) {
+  CHECK_F32_CUDA(x); CHECK_CONTIG(x); CHECK_F32_CUDA(w); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 2 && x.size(3) == w.size(1), "head_fwd: x [N,H,W,C], w [O,C]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), HW = (int)(x.size(1) * x.size(2)), C = (int)x.size(3), O = (int)w.size(0);
+  auto pooled = torch::empty({NB, C}, x.options());
+  auto logits = torch::empty({NB, O}, x.options());
+  fb::head_fwd(fptr(x), fptr(w), opt_ptr(bias), fptr_mut(pooled), fptr_mut(logits), NB, HW, C, O, cur_stream());
+  return {logits, pooled};
+}
+Tensor head_bwd(Tensor dlogits, Tensor w, int64_t H, int64_t W) {   // -> dx [N,H,W,C]
+  CHECK_F32_CUDA(dlogits); CHECK_CONTIG(dlogits); CHECK_F32_CUDA(w); CHECK_CONTIG(w);
+  c10::cuda::CUDAGuard guard(dlogits.device());
+  const int NB = (int)dlogits.size(0), O = (int)dlogits.size(1), C = (int)w.size(1);
+  auto dx = torch::empty({NB, H, W, C}, dlogits.options());
+  fb::head_bwd(fptr(dlogits), fptr(w), fptr_mut(dx), NB, (int)(H * W), C, O, cur_stream());
+  return dx;
+}
 Tensor avgpool_nhwc(Tensor x) {   // [N,H,W,C] -> [N,C]
   CHECK_F32_CUDA(x); CHECK_CONTIG(x);
   c10::cuda::CUDAGuard guard(x.device());
@@ -340,6 +359,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lbfgs_two_loop", &lbfgs_two_loop);
   m.def("normalize_u8", &normalize_u8);
   m.def("col_stats", &col_stats);
+  m.def("head_fwd", &head_fwd);
+  m.def("head_bwd", &head_bwd);
   m.def("bn_elu_fwd", &bn_elu_fwd);
   m.def("bn_elu_bwd", &bn_elu_bwd);
   m.def("avgpool_nhwc", &avgpool_nhwc);

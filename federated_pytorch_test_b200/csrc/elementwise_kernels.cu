@@ -542,6 +542,67 @@ void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_
   launch_pdl(avgpool_kernel, dim3((NB * C + 255) / 256), dim3(256), 0, s, x, out, NB, HW, C);
   check_launch("avgpool_nhwc");
 }
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (opt-in, FEDB200_HEAD_FUSED=1; written after this round's GPU budget was spent): classifier head
+// avg_pool(window) -> flatten -> Linear in ONE true-fp32 kernel per direction (SURVEY G4 + G5, simple_models.py:213-216).
+// The library path is avgpool (4 us) + a SIMT sgemm (13 us) for a 128x10x512 problem; here one block per sample pools
+// its [HW, C] map into shared memory and eight warps produce the O <= 32 logits with FMA chains + shuffle reductions.
+// ------------------------------------------------------------------------------------------------
+constexpr int HEAD_THREADS = 256;
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                float* __restrict__ pooled, float* __restrict__ logits, int HW, int C, int O) {
+  extern __shared__ float sp[];                    // pooled[C]
+  const int n = blockIdx.x;
+  const float inv = 1.f / float(HW);
+  const float* xn = x + size_t(n) * HW * C;
+  for (int c = threadIdx.x; c < C; c += HEAD_THREADS) {
+    float s = 0.f;
+    for (int k = 0; k < HW; ++k) s += xn[size_t(k) * C + c];
+    s *= inv;
+    sp[c] = s;
+    pooled[size_t(n) * C + c] = s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < O; o += HEAD_THREADS / 32) {
+    const float* wo = w + size_t(o) * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(sp[c], wo[c], acc);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) logits[size_t(n) * O + o] = acc + (bias != nullptr ? bias[o] : 0.f);
+  }
+}
+// dx[n, k, c] = (1/HW) * sum_o dlogits[n, o] * w[o, c]
+__global__ void __launch_bounds__(HEAD_THREADS)
+head_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ w, float* __restrict__ dx, int HW, int C,
+                int O) {
+  __shared__ float dl[32];
+  const int n = blockIdx.x;
+  if (threadIdx.x < O) dl[threadIdx.x] = dlogits[size_t(n) * O + threadIdx.x];
+  __syncthreads();
+  const float inv = 1.f / float(HW);
+  float* dxn = dx + size_t(n) * HW * C;
+  for (int c = threadIdx.x; c < C; c += HEAD_THREADS) {
+    float g = 0.f;
+    for (int o = 0; o < O; ++o) g = fmaf(dl[o], w[size_t(o) * C + c], g);
+    g *= inv;
+    for (int k = 0; k < HW; ++k) dxn[size_t(k) * C + c] = g;
+  }
+}
+void head_fwd(const float* x, const float* w, const float* bias, float* pooled, float* logits, int NB, int HW, int C, int O,
+              cudaStream_t s) {
+  if (O > 32) throw std::runtime_error("fedb200: head_fwd supports at most 32 outputs");
+  head_fwd_kernel<<<NB, HEAD_THREADS, C * sizeof(float), s>>>(x, w, bias, pooled, logits, HW, C, O);
+  check_launch("head_fwd");
+}
+void head_bwd(const float* dlogits, const float* w, float* dx, int NB, int HW, int C, int O, cudaStream_t s) {
+  if (O > 32) throw std::runtime_error("fedb200: head_bwd supports at most 32 outputs");
+  head_bwd_kernel<<<NB, HEAD_THREADS, 0, s>>>(dlogits, w, dx, HW, C, O);
+  check_launch("head_bwd");
+}
+
 __global__ void __launch_bounds__(256)
 avgpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int NB, int HW, int C) {
   pdl_prologue();

@@ -90,6 +90,10 @@ void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const
 bool bn_elu_bwd_fused(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
                       const float* gamma, const float* beta, float* sums, float* dy, float* dres, float* dgamma,
                       float* dbeta, int M, int C, int act, cudaStream_t s);
+// experimental fused classifier head: avg-pool over HW + Linear (true fp32), O <= 32 outputs
+void head_fwd(const float* x, const float* w, const float* bias, float* pooled, float* logits, int NB, int HW, int C, int O,
+              cudaStream_t s);
+void head_bwd(const float* dlogits, const float* w, float* dx, int NB, int HW, int C, int O, cudaStream_t s);
 void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_t s);
 void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaStream_t s);
 void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, int kw, cudaStream_t s);

@@ -377,7 +377,34 @@ class _AvgPoolNHWC(torch.autograd.Function):
         return dx.permute(0, 3, 1, 2)
 
 
+HEAD_FUSED = os.environ.get("FEDB200_HEAD_FUSED", "0") == "1"   # experimental, see tests/test_gpu_experimental.py
+
+
+class _PoolLinear(torch.autograd.Function):
+    """avg_pool over the whole map + Linear in one true-fp32 kernel per direction (experimental, opt-in)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        xn = _nhwc(x)
+        logits, pooled = ext().head_fwd(xn, weight.contiguous(), bias)
+        ctx.save_for_backward(weight, pooled)
+        ctx.hw = (xn.shape[1], xn.shape[2])
+        ctx.has_bias = bias is not None
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        weight, pooled = ctx.saved_tensors
+        dl = dlogits.contiguous()
+        dx = ext().head_bwd(dl, weight.contiguous(), ctx.hw[0], ctx.hw[1]).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
+        dw = dl.t() @ pooled if ctx.needs_input_grad[1] else None          # only when the classifier block is the active one
+        db = dl.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
 def pool_linear(x, linear: nn.Linear, window: int) -> torch.Tensor:
+    if HEAD_FUSED and linear.out_features <= 32:
+        return _PoolLinear.apply(x, linear.weight, linear.bias)
     pooled = _AvgPoolNHWC.apply(x)                     # global average over the window x window map
     return F.linear(pooled, linear.weight, linear.bias)  # 128x512x10: true fp32, as in the reference
 

@@ -73,3 +73,26 @@ def test_fused_bn_backward_equals_two_pass_oracle(C, M, res, act):
     torch.testing.assert_close(db, br.grad, rtol=2e-3, atol=2e-2)
     if res:
         torch.testing.assert_close(dres, rr.grad, rtol=1e-4, atol=1e-5)
+
+
+# run with FEDB200_HEAD_FUSED=1
+@pytest.mark.parametrize("B,C,O", [(128, 512, 10), (32, 512, 10), (7, 256, 3)])
+def test_fused_classifier_head(B, C, O):
+    torch.manual_seed(B + C)
+    lin = nn.Linear(C, O).to(DEV)
+    x = torch.randn(B, C, 4, 4, device=DEV, requires_grad=True)
+    e = cuda_ops.ext()
+    logits, pooled = e.head_fwd(x.detach().permute(0, 2, 3, 1).contiguous(), lin.weight, lin.bias)
+    ref = F.linear(F.avg_pool2d(x, 4).reshape(B, -1), lin.weight, lin.bias)
+    torch.testing.assert_close(logits, ref, rtol=1e-5, atol=1e-5)
+    g = torch.randn_like(ref)
+    (rx,) = torch.autograd.grad(ref, x, g)
+    dx = e.head_bwd(g.contiguous(), lin.weight, 4, 4).permute(0, 3, 1, 2)
+    torch.testing.assert_close(dx, rx, rtol=1e-5, atol=1e-6)
+    if os.environ.get("FEDB200_HEAD_FUSED", "0") == "1":
+        y = cuda_ops.pool_linear(x, lin, 4)
+        gx, gw, gb = torch.autograd.grad(y, (x, lin.weight, lin.bias), g)
+        rx2, rw, rb = torch.autograd.grad(F.linear(F.avg_pool2d(x, 4).reshape(B, -1), lin.weight, lin.bias), (x, lin.weight, lin.bias), g)
+        torch.testing.assert_close(gx, rx2, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(gw, rw, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(gb, rb, rtol=1e-5, atol=1e-5)
