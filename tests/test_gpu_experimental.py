@@ -27,7 +27,7 @@ def rel_err(a, b):
 # VAE encoder (simple_models.py:249-255) and CPC encoder incl. the dilated first layer (:441-451)
 @pytest.mark.parametrize("B,H,Ci,Co,k,s,p,d", [
     (16, 32, 3, 12, 4, 2, 1, 1), (16, 16, 12, 24, 4, 2, 1, 1), (16, 8, 24, 48, 4, 2, 1, 1), (16, 4, 48, 96, 4, 2, 1, 1),
-    (32, 32, 8, 8, 4, 2, 1, 1), (32, 32, 8, 8, 4, 2, 3, 2), (32, 32, 8, 8, 4, 2, 6, 4), (32, 16, 40, 64, 4, 2, 1, 1),
+    (32, 32, 8, 8, 4, 2, 1, 1), (32, 32, 8, 8, 4, 2, 3, 2), (32, 32, 8, 8, 4, 2, 6, 4), (32, 32, 8, 8, 4, 2, 12, 8), (32, 32, 8, 8, 4, 2, 24, 16), (32, 16, 40, 64, 4, 2, 1, 1),
     (32, 8, 64, 128, 4, 2, 1, 1), (32, 4, 128, 256, 4, 2, 1, 1)])
 @pytest.mark.parametrize("act", [True, False])
 def test_conv_bias_act_forward_backward(B, H, Ci, Co, k, s, p, d, act):
