@@ -216,3 +216,39 @@ def test_two_process_gloo_equals_single_process(tmp_path):
         assert a.split("=")[:-1] == b.split("=")[:-1]
         assert float(a.rsplit("=", 1)[1]) == pytest.approx(float(b.rsplit("=", 1)[1]), rel=1e-4)
     torch.testing.assert_close(got["flat"], eng.replicas[0].arenas["net"].data, rtol=1e-4, atol=1e-6)
+
+
+def _coresident_worker(rank, world, port, out, K, algo):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    mod = federated_multi if algo == "fedavg" else consensus_multi
+    extra = {} if algo == "fedavg" else dict(bb_update=True)
+    lines = []
+    cfg = mod.Config(K=K, Nloop=1, Nadmm=2, max_minibatches=2, check_results=False, use_cuda=False, **TINY, **extra)
+    eng = mod.run(cfg, log=lines.append)
+    if rank == 0:
+        torch.save({"lines": lines, "local": [r.ck for r in eng.replicas]}, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("algo", ["fedavg", "admm"])
+def test_co_resident_replicas_over_two_ranks_match_single_process(tmp_path, algo):
+    """K = 4 workers on 2 processes (two co-resident replicas per rank, gloo): same residual trace as the
+    single-process K = 4 run — the K > #GPUs placement of SURVEY §2.8, including the Barzilai-Borwein rho replay."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r0.pt")
+    port = 31500 + (os.getpid() % 2000) + (11 if algo == "admm" else 0)
+    mp.spawn(_coresident_worker, args=(2, port, out, 4, algo), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    assert got["local"] == [0, 2]
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    mod = federated_multi if algo == "fedavg" else consensus_multi
+    extra = {} if algo == "fedavg" else dict(bb_update=True)
+    _, lines = _run(mod, K=4, Nloop=1, Nadmm=2, max_minibatches=2, check_results=False, use_cuda=False, **extra)
+    key = "dual (" if algo == "fedavg" else "block=["
+    a = [l for l in got["lines"] if l.startswith(key)]
+    b = [l for l in lines if l.startswith(key)]
+    assert len(a) == len(b) == 10
+    for x, y in zip(a, b):
+        assert float(x.rsplit("=", 1)[1]) == pytest.approx(float(y.rsplit("=", 1)[1]), rel=1e-3, abs=1e-9), (x, y)
