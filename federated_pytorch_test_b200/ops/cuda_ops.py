@@ -297,8 +297,8 @@ class _ConvBnAct(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------
 # conv + bias (+ ELU) of the VAE / CPC networks: forward on the implicit-GEMM kernel, backward on ATen.
-# EXPERIMENTAL in this round (written after the GPU budget was spent: numerics not yet confirmed on a B200), therefore
-# opt-in: FEDB200_CONV_ACT=1.  tests/test_gpu_experimental.py holds the checks to run before flipping the default.
+# Opt-in in this round (FEDB200_CONV_ACT=1): the kernel-level checks of tests/test_gpu_experimental.py pass on a B200
+# (profiles/r1_run22_*), the VAE / CPC drivers have not been run with it yet.
 # ----------------------------------------------------------------------------
 CONV_ACT = os.environ.get("FEDB200_CONV_ACT", "0") == "1"
 

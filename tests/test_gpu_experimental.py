@@ -1,6 +1,6 @@
-"""GPU checks of code paths that were written after this round's GPU budget was spent and are therefore OPT-IN
-(environment switches, default off).  They are skipped unless ``FEDB200_EXPERIMENTAL=1`` so that the default suite only
-contains paths that have been confirmed on a B200; run them first thing next round:
+"""GPU checks of the OPT-IN code paths (environment switches, default off).  They were run once on a B200 at the end
+of round 1 (32 passed, profiles/r1_run22_pytest_experimental.log); the switches stay off until the drivers and bench.py
+have been exercised with them, so this module is skipped unless ``FEDB200_EXPERIMENTAL=1``:
 
     FEDB200_EXPERIMENTAL=1 FEDB200_CONV_ACT=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
 """
