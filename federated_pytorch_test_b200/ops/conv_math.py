@@ -71,3 +71,43 @@ def conv2x2_oracle(x_nhwc: torch.Tensor, w_krsc: torch.Tensor) -> torch.Tensor:
     """ATen oracle of the injected convolution (CPU tests, fall-back)."""
     x = F.pad(x_nhwc.permute(0, 3, 1, 2), (0, 1, 0, 1))
     return F.conv2d(x, w_krsc.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# ConvTranspose2d(k=4, stride=2, padding=1) — the VAE decoders (SURVEY G7, /root/reference/src/simple_models.py:262-265,
+# :336-340) — as ONE 3x3 / pad 1 / stride 1 convolution with 4*C_out output channels + the same pixel shuffle:
+#     y[n, 2i+ph, 2j+pw, co] = sum_{t_r,t_s in {0,1,2}} sum_ci x[n, i+t_r-1, j+t_s-1, ci] * Wp[(ph,pw,co), t_r, t_s, ci]
+# phase 0 takes filter rows 3 (offset -1) and 1 (offset 0), phase 1 takes rows 2 (offset 0) and 0 (offset +1); the other
+# window position of each phase is zero (4 of 9 taps populated per phase).
+# ------------------------------------------------------------------------------------------------
+_TAP4 = {(0, 0): 3, (0, 1): 1, (1, 1): 2, (1, 2): 0}      # (phase, window position) -> transposed-filter index
+
+
+def pack_convT_s2_weight(w_iokk: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d weight ``[C_in, C_out, 4, 4]`` -> KRSC filter ``[4*C_out, 3, 3, C_in]`` of the equivalent conv."""
+    Ci, Co, kh, kw = w_iokk.shape
+    assert kh == 4 and kw == 4, "phase decomposition implemented for ConvTranspose2d(k=4, stride=2, padding=1)"
+    zero = w_iokk.new_zeros(Co, Ci)
+    taps = []
+    for ph in (0, 1):
+        for pw in (0, 1):
+            for tr in (0, 1, 2):
+                for ts in (0, 1, 2):
+                    r, s_ = _TAP4.get((ph, tr)), _TAP4.get((pw, ts))
+                    taps.append(w_iokk[:, :, r, s_].t() if (r is not None and s_ is not None) else zero)   # [Co, Ci]
+    sel = torch.stack(taps, dim=0).reshape(2, 2, 3, 3, Co, Ci)                   # ph pw tr ts co ci
+    return sel.permute(0, 1, 4, 2, 3, 5).reshape(4 * Co, 3, 3, Ci).contiguous()
+
+
+def convT_s2(x_nhwc: torch.Tensor, w_packed: torch.Tensor, conv3x3: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]
+             ) -> torch.Tensor:
+    """x ``[N, H, W, Ci]`` -> ``[N, 2H, 2W, Co]``; ``conv3x3(x, w)`` = 3x3 / pad 1 / stride 1 convolution (bias and
+    activation, if any, are applied by the caller's ``conv3x3`` on the 4*Co phase-major channels)."""
+    N, H, W, _ = x_nhwc.shape
+    Co = w_packed.shape[0] // 4
+    y = conv3x3(x_nhwc, w_packed)                                    # [N, H, W, 4*Co]  (ph, pw, co)
+    return y.view(N, H, W, 2, 2, Co).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * H, 2 * W, Co)
+
+
+def conv3x3_oracle(x_nhwc: torch.Tensor, w_krsc: torch.Tensor) -> torch.Tensor:
+    return F.conv2d(x_nhwc.permute(0, 3, 1, 2), w_krsc.permute(0, 3, 1, 2), None, 1, 1).permute(0, 2, 3, 1).contiguous()

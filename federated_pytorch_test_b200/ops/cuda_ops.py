@@ -348,7 +348,47 @@ class _ConvAct(torch.autograd.Function):
         return (dx if need_x else None), (dw if need_w else None), (db if need_b else None), None, None, None, None
 
 
-def conv_act(x: torch.Tensor, conv: nn.Conv2d, act: bool = True) -> torch.Tensor:
+def conv_transpose_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
+    """ConvTranspose2d(k=4, stride=2, padding=1) of the VAE decoders as one 3x3 convolution with 4*C_out
+    phase channels + pixel shuffle (conv_math.pack_convT_s2_weight).  Same opt-in switch as conv_act."""
+    if not CONV_ACT or not isinstance(conv, nn.ConvTranspose2d) or x.dim() != 4 or x.dtype != torch.float32:
+        return False
+    if (tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), tuple(conv.output_padding), tuple(conv.dilation),
+            conv.groups) != ((4, 4), (2, 2), (1, 1), (0, 0), (1, 1), 1):
+        return False
+    H, W, Ci = x.shape[2], x.shape[3], conv.in_channels
+    return Ci % 4 == 0 and bool(ext().conv_supported(H, W, Ci, 1))
+
+
+class _ConvTransposeAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        xn = _nhwc(x)
+        wp = conv_math.pack_convT_s2_weight(weight)
+        b4 = bias.repeat(4) if bias is not None else None          # phase-major channels (ph, pw, co)
+        e = ext()
+        out = conv_math.convT_s2(xn, wp, lambda a, w: e.conv2d_nhwc_bias_act(a, w, b4, bool(act), 1, 1, 1))
+        ctx.save_for_backward(x, weight, out)
+        ctx.cfg = (act, bias is not None)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, out = ctx.saved_tensors
+        act, has_bias = ctx.cfg
+        d = _nhwc(dout)
+        if act:
+            d = d * torch.where(out > 0, torch.ones_like(out), out + 1.0)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and has_bias
+        dx, dw, db = torch.ops.aten.convolution_backward(
+            d.permute(0, 3, 1, 2), x, weight, [weight.shape[1]] if has_bias else None, [2, 2], [1, 1], [1, 1], True, [0, 0], 1,
+            [bool(need_x), bool(need_w), bool(need_b)])
+        return (dx if need_x else None), (dw if need_w else None), (db if need_b else None), None
+
+
+def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor:
+    if isinstance(conv, nn.ConvTranspose2d):
+        return _ConvTransposeAct.apply(x, conv.weight, conv.bias, bool(act))
     return _ConvAct.apply(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0], bool(act))
 
 

@@ -78,7 +78,7 @@ def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor
     if _use_fast(x):
         from . import cuda_ops
 
-        if cuda_ops.conv_act_supported(x, conv):
+        if cuda_ops.conv_act_supported(x, conv) or cuda_ops.conv_transpose_act_supported(x, conv):
             return cuda_ops.conv_act(x, conv, act)
     y = conv(x)
     return F.elu(y) if act else y

@@ -26,3 +26,15 @@ def test_packed_filter_has_nine_of_sixteen_taps():
     w = torch.ones(5, 3, 3, 7)
     wp = conv_math.pack_dgrad_s2_weight(w)
     assert int((wp != 0).sum()) == 9 * 5 * 7
+
+
+@pytest.mark.parametrize("N,H,Ci,Co", [(2, 2, 96, 48), (3, 4, 8, 12), (1, 8, 12, 3), (2, 16, 4, 3)])
+def test_conv_transpose_k4_s2_p1_as_one_conv_plus_pixel_shuffle(N, H, Ci, Co):
+    g = torch.Generator().manual_seed(H + Ci + Co)
+    x = torch.randn(N, Ci, H, H, generator=g, dtype=torch.float64)
+    w = torch.randn(Ci, Co, 4, 4, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, w, None, stride=2, padding=1)
+    wp = conv_math.pack_convT_s2_weight(w)
+    assert wp.shape == (4 * Co, 3, 3, Ci)
+    y = conv_math.convT_s2(x.permute(0, 2, 3, 1).contiguous(), wp, conv_math.conv3x3_oracle)
+    torch.testing.assert_close(y.permute(0, 3, 1, 2), ref, rtol=1e-10, atol=1e-10)

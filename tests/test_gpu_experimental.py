@@ -96,3 +96,22 @@ def test_fused_classifier_head(B, C, O):
         torch.testing.assert_close(gx, rx2, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(gw, rw, rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(gb, rb, rtol=1e-5, atol=1e-5)
+
+
+# VAE decoders (simple_models.py:262-265): ConvTranspose2d(k=4, s=2, p=1) = one 3x3 conv with 4*Co phase channels
+@pytest.mark.parametrize("B,H,Ci,Co", [(16, 2, 96, 48), (16, 4, 48, 24), (16, 8, 24, 12), (16, 16, 12, 3)])
+@pytest.mark.parametrize("act", [True, False])
+def test_conv_transpose_bias_act_forward_backward(B, H, Ci, Co, act):
+    torch.manual_seed(B + H + Ci + Co)
+    conv = nn.ConvTranspose2d(Ci, Co, 4, stride=2, padding=1).to(DEV)
+    x = torch.randn(B, Ci, H, H, device=DEV, requires_grad=True)
+    assert cuda_ops.conv_transpose_act_supported(x, conv), "set FEDB200_CONV_ACT=1"
+    y = cuda_ops.conv_act(x, conv, act)
+    ref = conv(x)
+    ref = F.elu(ref) if act else ref
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 3e-3
+    g = torch.randn_like(ref)
+    gx, gw, gb = torch.autograd.grad(y, (x, conv.weight, conv.bias), g)
+    rx, rw, rb = torch.autograd.grad(ref, (x, conv.weight, conv.bias), g)
+    assert rel_err(gx, rx) < 5e-3 and rel_err(gw, rw) < 5e-3 and rel_err(gb, rb) < 5e-3

@@ -10,7 +10,7 @@ LOG=gpurun_out/next_round_validate.log
 echo "=== default suite" >> $LOG
 timeout 300 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -5 >> $LOG
 echo "=== experimental: conv + bias + ELU (VAE / CPC)" >> $LOG
-FEDB200_EXPERIMENTAL=1 FEDB200_CONV_ACT=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k conv_bias_act 2>&1 | tail -8 >> $LOG
+FEDB200_EXPERIMENTAL=1 FEDB200_CONV_ACT=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k "conv_bias_act or conv_transpose" 2>&1 | tail -8 >> $LOG
 echo "=== experimental: fused BN backward" >> $LOG
 FEDB200_EXPERIMENTAL=1 FEDB200_BN_BWD_FUSED=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k fused_bn 2>&1 | tail -8 >> $LOG
 echo "=== experimental: fused classifier head" >> $LOG
