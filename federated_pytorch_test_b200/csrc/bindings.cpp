@@ -241,6 +241,21 @@ Tensor conv2d_nhwc_sized(Tensor x, Tensor w, c10::optional<Tensor> stats, int64_
   return y;
 }
 
+// y += conv(x, w), in place (experimental)
+Tensor conv2d_nhwc_accumulate(Tensor x, Tensor w, Tensor y, int64_t stride, int64_t pad, int64_t dil) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_F32_CUDA(y); CHECK_CONTIG(x); CHECK_CONTIG(w); CHECK_CONTIG(y);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && y.dim() == 4 && x.size(3) == w.size(3), "conv2d_nhwc_accumulate: x [N,H,W,Ci], w [Co,kh,kw,Ci]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), Ci = (int)x.size(3);
+  const int Co = (int)w.size(0), kh = (int)w.size(1), kw = (int)w.size(2);
+  const int Ho = (H + 2 * (int)pad - (int)dil * (kh - 1) - 1) / (int)stride + 1;
+  const int Wo = (W + 2 * (int)pad - (int)dil * (kw - 1) - 1) / (int)stride + 1;
+  TORCH_CHECK(y.size(0) == NB && y.size(1) == Ho && y.size(2) == Wo && y.size(3) == Co, "conv2d_nhwc_accumulate: y must be [N,Ho,Wo,Co]");
+  fb::conv2d_nhwc_accumulate_tf32(fptr(x), fptr(w), fptr_mut(y), NB, H, W, Ci, Co, kh, kw, (int)stride, (int)pad, (int)dil, Ho, Wo,
+                                  cur_stream());
+  return y;
+}
+
 // conv + bias (+ ELU) in one kernel: the bias-carrying convolutions of the VAE / CPC networks
 Tensor conv2d_nhwc_bias_act(Tensor x, Tensor w, c10::optional<Tensor> bias, bool act, int64_t stride, int64_t pad, int64_t dil) {
   CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
@@ -373,6 +388,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv2d_nhwc", &conv2d_nhwc);
   m.def("conv2d_nhwc_sized", &conv2d_nhwc_sized);
   m.def("conv2d_nhwc_bias_act", &conv2d_nhwc_bias_act);
+  m.def("conv2d_nhwc_accumulate", &conv2d_nhwc_accumulate);
   m.def("cross_entropy_fwd", &cross_entropy_fwd);
   m.def("cross_entropy_bwd", &cross_entropy_bwd);
   m.def("vae_loss_fwd", &vae_loss_fwd);

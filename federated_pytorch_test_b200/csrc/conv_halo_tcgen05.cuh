@@ -24,6 +24,7 @@ struct HaloParams {
   int a_box_bytes;         // 128 * Wp * R
   int box_h;               // image rows per TMA box (the halo tile is fetched as ceil(R / box_h) boxes issued back to back)
   int use_base_offset;     // experiment switch: encode (addr>>7)&7 in the descriptor's base_offset field
+  int accumulate;          // weight-stationary kernel: out += result (read-modify-write epilogue)
   int dbg;                 // profiling ablations (FEDB200_DBG): 1 = no activation TMA loads, 2 = no MMAs, 4 = no stores
   float* out;              // [NB*H*W, C_out]
   float* stats;            // [2*C_out] or nullptr

@@ -196,8 +196,15 @@ conv3x3_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int i = 0; i < 8; ++i) {
           const int r = i * 4 + (lane >> 3), cq = lane & 7;
           const int off = __shfl_sync(0xffffffffu, out_off, r);
-          const float4 val = *reinterpret_cast<const float4*>(my_scratch + r * WS_SCR_LD + cq * 4);
-          if (off >= 0 && !(p.dbg & 4)) *reinterpret_cast<float4*>(p.out + off + c0 + cq * 4) = val;
+          float4 val = *reinterpret_cast<const float4*>(my_scratch + r * WS_SCR_LD + cq * 4);
+          if (off >= 0 && !(p.dbg & 4)) {
+            float4* dst = reinterpret_cast<float4*>(p.out + off + c0 + cq * 4);
+            if (p.accumulate) {          // fused residual-gradient accumulation: out already holds the other branch
+              const float4 old = *dst;
+              val.x += old.x; val.y += old.y; val.z += old.z; val.w += old.w;
+            }
+            *dst = val;
+          }
         }
         if (p.stats != nullptr) {
           float s1 = 0.f, s2 = 0.f;

@@ -47,6 +47,9 @@ void linear_tf32(const float* x, const float* w, const float* bias, float* out, 
 bool conv_geometry_supported(int H_out, int W_out, int C_in, int stride);
 void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
                       int kh, int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream);
+// y += conv(x, w) (experimental: residual-gradient accumulation fused into the data-gradient convolution)
+void conv2d_nhwc_accumulate_tf32(const float* x, const float* w, float* y, int NB, int H, int W, int C_in, int C_out, int kh,
+                                 int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream);
 // same kernel with bias + optional ELU in the epilogue (no statistics, no split-K): VAE / CPC convolutions
 void conv2d_nhwc_bias_act_tf32(const float* x, const float* w, const float* bias, int act, float* y, int NB, int H, int W,
                                int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,

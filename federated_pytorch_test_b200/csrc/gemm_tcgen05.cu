@@ -415,8 +415,9 @@ static void launch_ws(const CUtensorMap& ta, const CUtensorMap& tb, const HaloPa
 }
 
 static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int accumulate = 0) {
   HaloParams p{};
+  p.accumulate = accumulate;
   p.NB = NB; p.H = H; p.W = W; p.Wp = W + 2;
   p.R = (p.Wp - 1 + 127 + 2 * p.Wp + 2) / p.Wp + 1;
   p.tiles_per_img = (H * p.Wp + IG_BLOCK_M - 1) / IG_BLOCK_M;
@@ -454,7 +455,7 @@ static void conv3x3_ws(const float* x, const float* w, float* y, float* stats, i
 // no BatchNorm statistics and no split-K in that case).
 static void conv2d_generic(const float* x, const float* w, float* y, float* stats, const float* bias, int act, int NB, int H,
                            int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
-                           cudaStream_t stream);
+                           cudaStream_t stream, int accumulate = 0);
 
 void conv2d_nhwc_tf32(const float* x, const float* w, float* y, float* stats, int NB, int H, int W, int C_in, int C_out,
                       int kh, int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream) {
@@ -475,9 +476,21 @@ void conv2d_nhwc_bias_act_tf32(const float* x, const float* w, const float* bias
   conv2d_generic(x, w, y, nullptr, bias, act, NB, H, W, C_in, C_out, kh, kw, stride, pad, dil, H_out, W_out, stream);
 }
 
+// y += conv(x, w): the residual-gradient accumulation of an identity-shortcut block fused into the data-gradient
+// convolution (experimental, FEDB200_SKIP_FUSED=1).  Weight-stationary kernel: read-modify-write epilogue; persistent
+// kernel: bulk tensor reduce-add.
+void conv2d_nhwc_accumulate_tf32(const float* x, const float* w, float* y, int NB, int H, int W, int C_in, int C_out, int kh,
+                                 int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream) {
+  if (ws_applicable(H, W, C_in, C_out, kh, kw, stride, pad, dil)) {
+    conv3x3_ws(x, w, y, nullptr, NB, H, W, C_in, C_out, stream, 1);
+    return;
+  }
+  conv2d_generic(x, w, y, nullptr, nullptr, 0, NB, H, W, C_in, C_out, kh, kw, stride, pad, dil, H_out, W_out, stream, 1);
+}
+
 static void conv2d_generic(const float* x, const float* w, float* y, float* stats, const float* bias, int act, int NB, int H,
                            int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int accumulate) {
   if (!conv_geometry_supported(H_out, W_out, C_in, stride))
     throw std::runtime_error("fedb200: conv geometry not supported by the tcgen05 path");
   const int rows = 128 / W_out;
@@ -500,6 +513,9 @@ static void conv2d_generic(const float* x, const float* w, float* y, float* stat
   p.stride = stride; p.pad = pad; p.dil = dil;
   p.out = y; p.ldo = C_out; p.bias = bias; p.act = act; p.stats = stats;
   p.k_splits = 1; p.kb_per_split = p.num_k_blocks; p.dbg = env_int("FEDB200_DBG", 0);
+  p.accumulate = accumulate;
+  if (accumulate && (pair || cl != 1 || env_int("FEDB200_KPS", 2) == 1 || env_int("FEDB200_PERSIST", 1) == 0))
+    throw std::runtime_error("fedb200: accumulating convolution needs the persistent kernel");
   // Split-K: the kernel is bound by what ONE SM can ingest (~40-60 B/cycle, profiles/r1_run8_*), so a grid that
   // leaves SMs idle (64 CTAs for layer3, 32 for layer4 with 128x256 tiles) wastes most of the chip.  Slice K until
   // ~one full wave of CTAs exists; partial tiles are reduced with red.global.add.v4 into a zeroed output and the
@@ -516,7 +532,7 @@ static void conv2d_generic(const float* x, const float* w, float* y, float* stat
       p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
       p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;   // no empty slices
       p.stats = nullptr;
-      cudaMemsetAsync(y, 0, size_t(M) * C_out * sizeof(float), stream);
+      if (!accumulate) cudaMemsetAsync(y, 0, size_t(M) * C_out * sizeof(float), stream);
     }
   }
   if (pair) dispatch2(bn, ta, tb, p, stream); else dispatch(bn, cl, ta, tb, p, stream);

@@ -268,7 +268,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             if (p.tma_store) fence_proxy_async();
             __syncwarp();
             if (p.tma_store && lane == 0 && !(p.dbg & 4)) {
-              if (p.k_splits > 1) tma_reduce_add_2d(&tmap_c, stage, c.n0 + c0, row0);
+              if (p.k_splits > 1 || p.accumulate) tma_reduce_add_2d(&tmap_c, stage, c.n0 + c0, row0);
               else tma_store_2d(&tmap_c, stage, c.n0 + c0, row0);
               tma_store_commit();
             }
@@ -276,7 +276,7 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
           if (!p.tma_store && row_ok && !(p.dbg & 4)) {
             // fallback for outputs whose row pitch is not a multiple of 16 B (e.g. 10-class logits)
             float* dst = p.out + size_t(row) * p.ldo + c.n0 + c0;
-            if (p.k_splits > 1) {
+            if (p.k_splits > 1 || p.accumulate) {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (c.n0 + c0 + j < p.N) atomicAdd(dst + j, f[j]);

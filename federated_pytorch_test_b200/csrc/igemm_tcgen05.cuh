@@ -46,6 +46,7 @@ struct IgemmParams {
   int k_splits;          // 1 = plain stores (+ fused stats); > 1 = reduction through L2 atomics, stats done by caller
   int dbg;               // profiling ablations (FEDB200_DBG, results are garbage): 1 = no TMA loads, 2 = no MMAs, 4 = no stores
   int m_tiles, n_tiles, total_tiles;   // persistent kernel: tile t -> (t % n_tiles, (t / n_tiles) % m_tiles, K split)
+  int accumulate;        // persistent kernel: out += result (bulk reduce-add / atomics) instead of out = result; no memset
   int tma_store;         // persistent kernel: write the output with bulk tensor stores / reduce-adds (needs ldo % 4 == 0)
   long long* trace;      // optional [16] clock64 stamps of CTA 0 (tools/trace_conv.py); nullptr in production
 };

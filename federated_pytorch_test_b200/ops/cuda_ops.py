@@ -296,6 +296,74 @@ class _ConvBnAct(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------
+# Identity-shortcut blocks: the gradient that reaches the block input is dgrad(conv1) + d(residual).  Autograd adds
+# the two with a separate elementwise kernel (11 `add` launches, 85 us per step, profiles/r1_run19_*).  Routing the
+# block input through the conv1 Function as a second, pass-through output hands BOTH gradients to one backward call,
+# which lets the data-gradient convolution accumulate straight into the residual gradient (read-modify-write epilogue
+# in the weight-stationary kernel, bulk reduce-add in the persistent kernel).  Opt-in: FEDB200_SKIP_FUSED=1.
+# ----------------------------------------------------------------------------
+SKIP_FUSED = os.environ.get("FEDB200_SKIP_FUSED", "0") == "1"
+
+
+class _ConvBnActSkip(torch.autograd.Function):
+    """``(ELU(BN_train(conv(x))), x)`` — the second output is the block input itself (no copy)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, stride, pad, eps, momentum):
+        e = ext()
+        xn = _nhwc(x)
+        wk = _krsc(weight)
+        Co = weight.shape[0]
+        stats, self_clean = _stats_buffer(weight, Co)
+        y = e.conv2d_nhwc(xn, wk, stats, stride, pad, 1)
+        out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, None, running_mean, running_var, eps, momentum, True, self_clean)
+        ctx.save_for_backward(xn, wk, y, mean, invstd, gamma, beta)
+        ctx.cfg = (stride, pad, tuple(weight.shape))
+        return out.permute(0, 3, 1, 2), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dout, dskip):
+        e = ext()
+        xn, wk, y, mean, invstd, gamma, beta = ctx.saved_tensors
+        stride, pad, wshape = ctx.cfg
+        need_x, need_w, need_g, need_b = ctx.needs_input_grad[:4]
+        dgamma = torch.zeros_like(gamma) if need_g else None
+        dbeta = torch.zeros_like(gamma) if need_b else None
+        dy, _ = e.bn_elu_bwd(_nhwc(dout), None, y, mean, invstd, gamma, beta, dgamma, dbeta, False, True)
+        kh = wshape[2]
+        dx = dw = None
+        if need_x:
+            wf = _flipped_weight(wk, need_w)
+            if dskip is not None:
+                acc = _nhwc(dskip)                       # the residual gradient of conv2's Function: ours alone
+                if not acc.is_contiguous():
+                    acc = acc.contiguous()
+                dxn = e.conv2d_nhwc_accumulate(dy, wf, acc, 1, kh - 1 - pad, 1)      # acc += dgrad(dy), in place
+            else:
+                dxn = e.conv2d_nhwc(dy, wf, None, 1, kh - 1 - pad, 1)
+            dx = dxn.permute(0, 3, 1, 2)
+        elif dskip is not None:
+            dx = dskip
+        if need_w:
+            dw = torch.ops.aten.convolution_backward(
+                dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
+                [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+        return dx, dw, dgamma, dbeta, None, None, None, None, None, None
+
+
+def conv_bn_act_skip_supported(x: torch.Tensor, conv: nn.Conv2d, bn: nn.BatchNorm2d) -> bool:
+    if not SKIP_FUSED or not conv_bn_act_supported(x, conv, bn):
+        return False
+    # stride-1 3x3 with matching channel counts (identity shortcut) and a 16-byte pixel pitch
+    return conv.stride[0] == 1 and conv.in_channels == conv.out_channels and conv.in_channels % 4 == 0 and x.requires_grad
+
+
+def conv_bn_act_skip(x, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    return _ConvBnActSkip.apply(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.stride[0],
+                                conv.padding[0], bn.eps, bn.momentum)
+
+
+# ----------------------------------------------------------------------------
 # conv + bias (+ ELU) of the VAE / CPC networks (SURVEY G6): forward on the implicit-GEMM kernel, backward on ATen.
 # Opt-in in this round (FEDB200_CONV_ACT=1): the kernel-level checks of tests/test_gpu_experimental.py pass on a B200
 # (profiles/r1_run22_*), the VAE / CPC drivers have not been run with it yet.

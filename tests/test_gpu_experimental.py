@@ -115,3 +115,45 @@ def test_conv_transpose_bias_act_forward_backward(B, H, Ci, Co, act):
     gx, gw, gb = torch.autograd.grad(y, (x, conv.weight, conv.bias), g)
     rx, rw, rb = torch.autograd.grad(ref, (x, conv.weight, conv.bias), g)
     assert rel_err(gx, rx) < 5e-3 and rel_err(gw, rw) < 5e-3 and rel_err(gb, rb) < 5e-3
+
+
+# run with FEDB200_SKIP_FUSED=1: identity-shortcut blocks accumulate dgrad(conv1) into the residual gradient in the
+# convolution epilogue (weight-stationary kernel for 64 ch @ 32x32, persistent kernel otherwise)
+@pytest.mark.parametrize("planes,H,B", [(64, 32, 8), (128, 16, 8), (256, 8, 16), (512, 4, 16), (64, 32, 3)])
+def test_identity_block_with_fused_residual_gradient(planes, H, B):
+    assert os.environ.get("FEDB200_SKIP_FUSED", "0") == "1", "set FEDB200_SKIP_FUSED=1"
+    from federated_pytorch_test_b200 import models
+    from federated_pytorch_test_b200.ops import functional as FX
+    torch.manual_seed(planes + H)
+    a = models.BasicBlock(planes, planes, 1).to(DEV)
+    b = models.BasicBlock(planes, planes, 1).to(DEV)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(B, planes, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    FX.set_fast_path(True)
+    oa = a(xa * 1.0)                   # non-leaf block input, as inside the network
+    FX.set_fast_path(False)
+    ob = b(xb * 1.0)
+    FX.set_fast_path(True)
+    assert rel_err(oa, ob) < 5e-3
+    go = torch.randn_like(ob)
+    oa.backward(go)
+    ob.backward(go)
+    assert rel_err(xa.grad, xb.grad) < 2e-2
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel_err(pa.grad, pb.grad) < 2e-2, n
+
+
+def test_accumulating_convolution_kernels():
+    """y += conv(x, w) through both kernels (weight-stationary: 64 ch @ 32x32; persistent: everything else)."""
+    e = cuda_ops.ext()
+    for B, H, C in ((4, 32, 64), (6, 16, 128), (16, 8, 256)):
+        g = torch.Generator(device=DEV).manual_seed(H + C)
+        x = torch.randn(B, H, H, C, device=DEV, generator=g)
+        w = torch.randn(C, 3, 3, C, device=DEV, generator=g) / math.sqrt(9 * C)
+        y0 = torch.randn(B, H, H, C, device=DEV, generator=g)
+        ref = y0.double() + F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), None, 1, 1).permute(0, 2, 3, 1)
+        y = y0.clone()
+        out = e.conv2d_nhwc_accumulate(x, w, y, 1, 1, 1)
+        assert out.data_ptr() == y.data_ptr()
+        assert rel_err(y, ref.float()) < 3e-3

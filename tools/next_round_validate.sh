@@ -13,6 +13,8 @@ echo "=== experimental: conv + bias + ELU (VAE / CPC)" >> $LOG
 FEDB200_EXPERIMENTAL=1 FEDB200_CONV_ACT=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k "conv_bias_act or conv_transpose" 2>&1 | tail -8 >> $LOG
 echo "=== experimental: fused BN backward" >> $LOG
 FEDB200_EXPERIMENTAL=1 FEDB200_BN_BWD_FUSED=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k fused_bn 2>&1 | tail -8 >> $LOG
+echo "=== experimental: fused residual-gradient accumulation" >> $LOG
+FEDB200_EXPERIMENTAL=1 FEDB200_SKIP_FUSED=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k "identity_block or accumulating" 2>&1 | tail -8 >> $LOG
 echo "=== experimental: fused classifier head" >> $LOG
 FEDB200_EXPERIMENTAL=1 FEDB200_HEAD_FUSED=1 timeout 300 python -m pytest tests/test_gpu_experimental.py -m gpu -q -p no:cacheprovider -k classifier_head 2>&1 | tail -8 >> $LOG
 echo "=== drivers with the experimental paths on" >> $LOG
@@ -23,5 +25,5 @@ echo "=== BN micro-benchmark, two-pass vs fused backward" >> $LOG
 echo "=== bench, default vs fused BN backward" >> $LOG
 timeout 200 python bench.py --steps 40 --warmup 5 2>&1 | tail -1 | cut -c1-220 >> $LOG
 FEDB200_BN_BWD_FUSED=1 timeout 200 python bench.py --steps 40 --warmup 5 2>&1 | tail -1 | cut -c1-220 >> $LOG
-FEDB200_BN_BWD_FUSED=1 FEDB200_HEAD_FUSED=1 timeout 200 python bench.py --steps 40 --warmup 5 2>&1 | tail -1 | cut -c1-220 >> $LOG
+FEDB200_BN_BWD_FUSED=1 FEDB200_HEAD_FUSED=1 FEDB200_SKIP_FUSED=1 timeout 200 python bench.py --steps 40 --warmup 5 2>&1 | tail -1 | cut -c1-220 >> $LOG
 tail -40 $LOG
