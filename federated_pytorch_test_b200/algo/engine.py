@@ -190,7 +190,7 @@ class Engine:
         task, cfg = self.task, self.cfg
         pre_loss = [None]
         if isinstance(opt, BlockAdam):
-            opt.set_penalty(pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2)
+            opt.set_penalty(pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2, pen.rho_dev)
 
             def closure():
                 opt.zero_grad()

@@ -51,8 +51,10 @@ class GraphedAdamStep:
         return loss.detach()
 
     def _pen_key(self, pen):
+        # a device-resident rho (adaptive ADMM) never invalidates the graph; a host-side one is baked into the launch
+        rho_key = ("dev", pen.rho_dev.data_ptr()) if pen.rho_dev is not None else ("host", float(pen.rho))
         return (pen.z.data_ptr() if pen.z is not None else 0, pen.y.data_ptr() if pen.y is not None else 0,
-                float(pen.rho), self.visit.lambda1, self.visit.lambda2)
+                rho_key, self.visit.lambda1, self.visit.lambda2)
 
     def _capture(self) -> None:
         before = cuda_ops.launch_count()
@@ -70,7 +72,7 @@ class GraphedAdamStep:
             self.pen_key = key
             self.graph = None
             self.calls = 0
-        opt.set_penalty(pen.z, pen.y, pen.rho, self.visit.lambda1, self.visit.lambda2)
+        opt.set_penalty(pen.z, pen.y, pen.rho, self.visit.lambda1, self.visit.lambda2, pen.rho_dev)
         for dst, src in zip(self.static, batch):
             if torch.is_tensor(dst):
                 if dst.shape != src.shape:

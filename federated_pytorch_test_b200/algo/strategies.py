@@ -35,7 +35,8 @@ class Penalty:
 
     z: Optional[torch.Tensor] = None
     y: Optional[torch.Tensor] = None
-    rho: float = 0.0
+    rho: float = 0.0                            # host mirror (logs, L-BFGS closures)
+    rho_dev: Optional[torch.Tensor] = None      # device-resident penalty read by the kernels (adaptive ADMM)
 
 
 class Strategy:
@@ -52,7 +53,9 @@ class Strategy:
 
     def begin_block(self, ci: int, N: int, xs: List[torch.Tensor]) -> None:
         self.ci, self.N, self.xs = ci, int(N), xs
-        self.z = torch.zeros_like(xs[0])  # Q6: restart from the origin on every block visit
+        # Q6: restart from the origin on every block visit.  The fused backend hands out a slice of a symmetric arena so
+        # that peers can broadcast their part of the new consensus vector straight into it (two-shot aggregation).
+        self.z = self.coll.zeros_like_block(xs[0], "z")
 
     def penalty(self, i: int) -> Penalty:
         return Penalty()
@@ -85,6 +88,9 @@ class FedAvg(Strategy):
         dual_sq = self.coll.fedavg_(self.xs, self.z, write_back=True)
         return {"dual": math.sqrt(max(float(dual_sq), 0.0)) / self.N}
 
+    def load_state(self, st: Dict[str, object]) -> None:
+        self.z.copy_(st["z"].to(self.z.device))
+
 
 class FedProx(Strategy):
     name = "fedprox"
@@ -104,6 +110,13 @@ class FedProx(Strategy):
         dual_sq, primal = self.coll.fedprox_(self.xs, self.z, rho)
         return {"dual": math.sqrt(max(float(dual_sq), 0.0)) / self.N, "primal": float(primal) / self.N}
 
+    def state(self) -> Dict[str, object]:
+        return {"z": self.z, "rho": self.rho}
+
+    def load_state(self, st: Dict[str, object]) -> None:
+        self.z.copy_(st["z"].to(self.z.device))
+        self.rho.copy_(st["rho"])
+
 
 @dataclass
 class BBConfig:
@@ -120,12 +133,17 @@ class ADMM(Strategy):
 
     def __init__(self, collective, topo, num_blocks: int, rho0: float = 0.1, bb: Optional[BBConfig] = None, log=print):
         super().__init__(collective, topo)
-        self.rho = torch.ones(num_blocks, 3) * rho0
+        self.rho = torch.ones(num_blocks, 3) * rho0          # host mirror of the reference's [L,3] table (column 0 used)
         self.bb = bb or BBConfig()
         self.ys: List[torch.Tensor] = []
         self.yhat0: List[torch.Tensor] = []
         self.x0: List[torch.Tensor] = []
         self.log = log
+        # the penalty the kernels read: one float per block in device memory.  The BB kernel rewrites it in place, the
+        # aggregation kernel and the fused Adam kernel read it — no host value is baked into a launch or a CUDA graph.
+        self.rho_dev: Optional[torch.Tensor] = None
+        if topo.device.type == "cuda":
+            self.rho_dev = torch.full((num_blocks,), float(rho0), dtype=torch.float32, device=topo.device)
 
     def begin_block(self, ci: int, N: int, xs: List[torch.Tensor]) -> None:
         super().begin_block(ci, N, xs)
@@ -134,14 +152,26 @@ class ADMM(Strategy):
             self.yhat0 = [x.clone() if self.bb.seed_yhat0_with_x else torch.zeros_like(x) for x in xs]
             self.x0 = [torch.zeros_like(x) for x in xs]
 
+    def _rho_slot(self) -> Optional[torch.Tensor]:
+        return self.rho_dev[self.ci: self.ci + 1] if self.rho_dev is not None else None
+
     def penalty(self, i: int) -> Penalty:
-        return Penalty(z=self.z, y=self.ys[i], rho=float(self.rho[self.ci, 0]))
+        return Penalty(z=self.z, y=self.ys[i], rho=float(self.rho[self.ci, 0]), rho_dev=self._rho_slot())
 
     def rho_mean(self) -> float:
         return float(self.rho.mean())
 
     def state(self) -> Dict[str, object]:
         return {"z": self.z, "y": self.ys, "rho": self.rho, "yhat0": self.yhat0, "x0": self.x0}
+
+    def load_state(self, st: Dict[str, object]) -> None:
+        self.z.copy_(st["z"].to(self.z.device))
+        self.rho.copy_(st["rho"])
+        if self.rho_dev is not None:
+            self.rho_dev.copy_(self.rho[:, 0].to(self.rho_dev.device))
+        for dst, src in (("ys", "y"), ("yhat0", "yhat0"), ("x0", "x0")):
+            for d, t in zip(getattr(self, dst), st.get(src) or []):
+                d.copy_(t.to(d.device))
 
     # -- adaptive rho ---------------------------------------------------------
     def _bb_update(self, nadmm: int) -> None:
@@ -152,43 +182,27 @@ class ADMM(Strategy):
         ``a=y-yhat0, b=x-z, c=x-x0`` the quantities it needs are
         ``d11 = a.a + 2 rho a.b + rho^2 b.b``, ``d12 = a.c + rho b.c``, ``d22 = c.c``,
         so six local dots per worker + one tiny gather reproduce the sequential
-        rule without serialising the GPUs.
+        rule without serialising the GPUs.  On B200 all of it — dots, gather through
+        the peer-mapped control pads, replay, ``yhat0``/``x0`` carry — is ONE kernel
+        (``csrc/comm_kernels.cu: bb_update_kernel``) that leaves the new rho in
+        device memory; the host only reads the log rows for the legacy print lines.
         """
         cfg = self.bb
-        rows = self.coll.bb_dots(self.xs, self.ys, self.yhat0, self.x0, self.z).double().cpu()
-        rho = float(self.rho[self.ci, 0])
-        rho_at_turn = []
+        rho_in = float(self.rho[self.ci, 0])
+        rows = self.coll.bb_update_(self.xs, self.ys, self.yhat0, self.x0, self.z, rho_in, self._rho_slot(), cfg)
         for ck in range(self.topo.K):
-            aa, ab, bb_, ac, bc, cc = (float(v) for v in rows[ck])
-            rho_at_turn.append(rho)
-            d11 = aa + 2.0 * rho * ab + rho * rho * bb_
-            d12 = ac + rho * bc
-            d22 = cc
+            d11, d12, d22, alpha, aSD, aMG, tested, rho_after = (float(v) for v in rows[ck])
             self.log("admm %d deltas=(%e,%e,%e)" % (nadmm, d11, d12, d22))
-            rhonew = rho
-            if abs(d12) > cfg.epsilon and d11 > cfg.epsilon and d22 > cfg.epsilon:
-                alpha = d12 / math.sqrt(d11 * d22)
-                alphaSD = d11 / d22
-                alphaMG = d12 / d22
-                alphahat = alphaMG if 2.0 * alphaMG > alphaSD else alphaSD - 0.5 * alphaMG
-                if alpha >= cfg.alphacorrmin and alphahat < cfg.rhomax:
-                    rhonew = alphahat
-                self.log("admm %d alphas=(%e,%e,%e)" % (nadmm, alpha, alphaSD, alphaMG))
-            rho = rhonew
-        self.rho[self.ci, 0] = rho
-        # carry forward: yhat0_k <- y_k + rho_k (x_k - z) with the rho in force at worker k's turn
-        for i, ck in enumerate(self.topo.local_workers):
-            r = rho_at_turn[ck]
-            torch.add(self.ys[i], self.xs[i] - self.z, alpha=r, out=self.yhat0[i])
-            self.x0[i].copy_(self.xs[i])
+            if tested:
+                self.log("admm %d alphas=(%e,%e,%e)" % (nadmm, alpha, aSD, aMG))
+        self.rho[self.ci, 0] = float(rows[self.topo.K - 1][7])
 
     def aggregate(self, nadmm: int) -> Dict[str, float]:
         if self.bb.enabled:
             if nadmm == 0:
-                for i in range(len(self.xs)):
-                    self.x0[i].copy_(self.xs[i])
+                self.coll.bb_seed_(self.xs, self.x0)
             elif nadmm % self.bb.period_T == 0:
                 self._bb_update(nadmm)
         rho = float(self.rho[self.ci, 0])
-        dual_sq, primal = self.coll.admm_(self.xs, self.ys, self.z, rho)
+        dual_sq, primal = self.coll.admm_(self.xs, self.ys, self.z, rho, self._rho_slot())
         return {"dual": math.sqrt(max(float(dual_sq), 0.0)) / self.N, "primal": float(primal) / self.N}

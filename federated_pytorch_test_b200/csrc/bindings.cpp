@@ -20,11 +20,12 @@ static const float* opt_ptr(const c10::optional<Tensor>& t) { return (t.has_valu
 
 // ---------------------------------------------------------------------------------------------- flat ops
 void adam_prox(Tensor x, Tensor g, Tensor m, Tensor v, Tensor step, double lr, double b1, double b2, double eps,
-               c10::optional<Tensor> z, c10::optional<Tensor> y, double rho, double l1, double l2) {
+               c10::optional<Tensor> z, c10::optional<Tensor> y, double rho, double l1, double l2,
+               c10::optional<Tensor> rho_dev) {
   CHECK_F32_CUDA(x); CHECK_CONTIG(x); CHECK_CONTIG(g); CHECK_CONTIG(m); CHECK_CONTIG(v);
   c10::cuda::CUDAGuard guard(x.device());
   fb::adam_prox(fptr_mut(x), fptr(g), fptr_mut(m), fptr_mut(v), step.data_ptr<int>(), (int)x.numel(), (float)lr, (float)b1,
-                (float)b2, (float)eps, opt_ptr(z), opt_ptr(y), (float)rho, (float)l1, (float)l2, cur_stream());
+                (float)b2, (float)eps, opt_ptr(z), opt_ptr(y), (float)rho, (float)l1, (float)l2, cur_stream(), opt_ptr(rho_dev));
 }
 void bump_step(Tensor step) {
   c10::cuda::CUDAGuard guard(step.device());
@@ -310,15 +311,21 @@ std::vector<Tensor> vae_loss_bwd(Tensor recon, Tensor x, Tensor mu, Tensor logva
 
 // ---------------------------------------------------------------------------------------------- collectives
 // Pointers are passed as integers: local tensors' data_ptr() or peer-mapped addresses from symmetric memory.
+static void fill_ctrl(uint32_t** dst, const std::vector<int64_t>& ctrl_ptrs, int world) {
+  for (int p = 0; p < world && p < (int)ctrl_ptrs.size(); ++p) dst[p] = reinterpret_cast<uint32_t*>(ctrl_ptrs[p]);
+}
 void block_reduce(int64_t mode, std::vector<int64_t> x_ptrs, std::vector<int64_t> y_ptrs, std::vector<int64_t> local_idx,
-                  Tensor z, int64_t n, double inv_scale, double rho, Tensor out, std::vector<int64_t> ctrl_ptrs,
-                  Tensor sync, int64_t world, int64_t rank, int64_t mc_x, int64_t mc_y) {
-  CHECK_F32_CUDA(z); CHECK_F32_CUDA(out);
-  TORCH_CHECK(out.numel() >= 4 + fb::COMM_MAX_LOCAL, "out too small");
+                  Tensor z, int64_t n, double rho, c10::optional<Tensor> rho_dev, Tensor out, Tensor scratch,
+                  std::vector<int64_t> ctrl_ptrs, Tensor sync, int64_t world, int64_t rank, int64_t mc_x, int64_t mc_y,
+                  int64_t mc_z, std::vector<int64_t> xw_ptrs, std::vector<int64_t> zw_ptrs, bool two_shot,
+                  int64_t max_blocks, double timeout_s) {
+  CHECK_F32_CUDA(z); CHECK_F32_CUDA(out); CHECK_F32_CUDA(scratch);
+  TORCH_CHECK(out.numel() >= fb::COMM_OUT_FLOATS && scratch.numel() >= fb::COMM_SCRATCH_FLOATS, "out / scratch too small");
   c10::cuda::CUDAGuard guard(z.device());
   fb::CommArgs a{};
   a.mode = (int)mode; a.K = (int)x_ptrs.size(); a.n_local = (int)local_idx.size(); a.world = (int)world; a.rank = (int)rank;
-  a.n = (int)n; a.inv_scale = (float)inv_scale; a.rho = (float)rho;
+  a.n = (int)n; a.rho = (float)rho; a.rho_dev = opt_ptr(rho_dev);
+  a.two_shot = two_shot ? 1 : 0; a.max_blocks = (int)max_blocks;
   TORCH_CHECK(a.K <= fb::COMM_MAX_K && a.n_local <= fb::COMM_MAX_LOCAL && a.world <= fb::COMM_MAX_WORLD, "block_reduce: limits exceeded");
   for (int k = 0; k < a.K; ++k) {
     a.x[k] = reinterpret_cast<const float*>(x_ptrs[k]);
@@ -328,13 +335,63 @@ void block_reduce(int64_t mode, std::vector<int64_t> x_ptrs, std::vector<int64_t
     a.xl[j] = reinterpret_cast<float*>(x_ptrs[local_idx[j]]);
     a.yl[j] = y_ptrs.empty() ? nullptr : reinterpret_cast<float*>(y_ptrs[local_idx[j]]);
   }
-  a.mc_x = reinterpret_cast<const float*>(mc_x);
-  a.mc_y = reinterpret_cast<const float*>(mc_y);
+  for (int p = 0; p < a.world; ++p) {
+    a.xw[p] = p < (int)xw_ptrs.size() ? reinterpret_cast<float*>(xw_ptrs[p]) : nullptr;
+    a.zw[p] = p < (int)zw_ptrs.size() ? reinterpret_cast<float*>(zw_ptrs[p]) : nullptr;
+  }
+  if (a.two_shot) {
+    if (a.mode == 0) {
+      TORCH_CHECK(mc_x != 0 || (int)xw_ptrs.size() == a.world, "two-shot FedAvg needs broadcast targets");
+    } else {
+      TORCH_CHECK(mc_z != 0 || (int)zw_ptrs.size() == a.world, "two-shot FedProx/ADMM needs peer-mapped z");
+    }
+  }
+  a.mc_x = reinterpret_cast<float*>(mc_x);
+  a.mc_y = reinterpret_cast<float*>(mc_y);
+  a.mc_z = reinterpret_cast<float*>(mc_z);
   a.z = z.data_ptr<float>();
   a.out = out.data_ptr<float>();
-  for (int p = 0; p < a.world && p < (int)ctrl_ptrs.size(); ++p) a.ctrl[p] = reinterpret_cast<uint32_t*>(ctrl_ptrs[p]);
+  a.scratch = scratch.data_ptr<float>();
+  fill_ctrl(a.ctrl, ctrl_ptrs, a.world);
   a.sync = reinterpret_cast<uint32_t*>(sync.data_ptr<int>());
+  a.timeout_cycles = (long long)(timeout_s * 1.9e9);
   fb::block_reduce_launch(a, cur_stream());
+}
+
+// Barzilai-Borwein update (consensus_multi.py:242-278) as one kernel; see BBArgs.
+void bb_update(std::vector<Tensor> xs, std::vector<Tensor> ys, std::vector<Tensor> yhat0s, std::vector<Tensor> x0s, Tensor z,
+               std::vector<int64_t> workers, int64_t K, Tensor rho_dev, Tensor log, Tensor scratch, Tensor out,
+               std::vector<int64_t> ctrl_ptrs, Tensor sync, int64_t world, int64_t rank, double epsilon, double alphacorrmin,
+               double rhomax, bool seed_only, int64_t max_blocks, double timeout_s) {
+  TORCH_CHECK(!xs.empty() && xs.size() == x0s.size() && xs.size() <= (size_t)fb::COMM_MAX_LOCAL, "bb_update: bad replica count");
+  CHECK_F32_CUDA(z); CHECK_F32_CUDA(rho_dev); CHECK_F32_CUDA(log); CHECK_F32_CUDA(scratch);
+  TORCH_CHECK(log.numel() >= 8 * K && scratch.numel() >= fb::BB_SCRATCH_FLOATS, "bb_update: log / scratch too small");
+  c10::cuda::CUDAGuard guard(z.device());
+  fb::BBArgs a{};
+  a.K = (int)K; a.n_local = (int)xs.size(); a.world = (int)world; a.rank = (int)rank; a.n = (int)xs[0].numel();
+  a.seed_only = seed_only ? 1 : 0; a.max_blocks = (int)max_blocks;
+  a.epsilon = (float)epsilon; a.alphacorrmin = (float)alphacorrmin; a.rhomax = (float)rhomax;
+  for (int j = 0; j < a.n_local; ++j) {
+    CHECK_F32_CUDA(xs[j]); CHECK_CONTIG(xs[j]); CHECK_CONTIG(x0s[j]);
+    TORCH_CHECK(xs[j].numel() == a.n && x0s[j].numel() == a.n, "bb_update: equal lengths required");
+    a.x[j] = fptr(xs[j]);
+    a.x0[j] = fptr_mut(x0s[j]);
+    if (!seed_only) {
+      CHECK_CONTIG(ys[j]); CHECK_CONTIG(yhat0s[j]);
+      a.y[j] = fptr(ys[j]);
+      a.yhat0[j] = fptr_mut(yhat0s[j]);
+    }
+    a.worker[j] = (int)workers[j];
+  }
+  a.z = fptr(z);
+  a.rho_dev = fptr_mut(rho_dev);
+  a.log = fptr_mut(log);
+  a.scratch = fptr_mut(scratch);
+  a.out = fptr_mut(out);
+  fill_ctrl(a.ctrl, ctrl_ptrs, a.world);
+  a.sync = reinterpret_cast<uint32_t*>(sync.data_ptr<int>());
+  a.timeout_cycles = (long long)(timeout_s * 1.9e9);
+  fb::bb_update_launch(a, cur_stream());
 }
 
 // ---------------------------------------------------------------------------------------------- CUDA IPC helpers
@@ -394,6 +451,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("vae_loss_fwd", &vae_loss_fwd);
   m.def("vae_loss_bwd", &vae_loss_bwd);
   m.def("block_reduce", &block_reduce);
+  m.def("bb_update", &bb_update);
   m.def("ipc_get_handle", &ipc_get_handle);
   m.def("ipc_open_handle", &ipc_open_handle);
   m.def("ipc_close_handle", &ipc_close_handle);

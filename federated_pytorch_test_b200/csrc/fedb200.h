@@ -60,7 +60,8 @@ void probe_launch(int kind, int grid, int smem_bytes, cudaStream_t stream);   //
 
 // ---- flat-vector kernels (flat_kernels.cu) ---------------------------------------------------------
 void adam_prox(float* x, const float* g, float* m, float* v, const int* step_dev, int n, float lr, float b1, float b2,
-               float eps, const float* z, const float* y, float rho, float l1, float l2, cudaStream_t s);
+               float eps, const float* z, const float* y, float rho, float l1, float l2, cudaStream_t s,
+               const float* rho_dev = nullptr);
 void bump_step(int* step_dev, cudaStream_t s);
 void l1_l2(const float* g, int n, float* out2, cudaStream_t s);
 void make_pair(const float* g, const float* gprev, const float* d, float t, float trust, float* y, float* sv, int n,
@@ -116,24 +117,74 @@ constexpr int COMM_MAX_K = 64;       // contributions (workers) per aggregation
 constexpr int COMM_MAX_LOCAL = 16;   // replicas hosted by one process
 constexpr int COMM_MAX_WORLD = 16;   // processes meeting through peer memory
 constexpr int COMM_THREADS = 512;
+constexpr int COMM_MAX_BLOCKS = 160; // CTAs per aggregation kernel (one per SM on a B200: 148)
+
+// Control pad (uint32 words; one pad per rank, mapped into every peer).  Flags hold the epoch of the aggregation that
+// last signalled them (monotonic, compared with >=), so nothing is ever reset.
+constexpr int PAD_FLAG_A = 0;                                                 // [COMM_MAX_BLOCKS][COMM_MAX_WORLD]  per-CTA: inputs final
+constexpr int PAD_FLAG_B = PAD_FLAG_A + COMM_MAX_BLOCKS * COMM_MAX_WORLD;     // [COMM_MAX_BLOCKS][COMM_MAX_WORLD]  per-CTA: reads / broadcasts done
+constexpr int PAD_FLAG_C = PAD_FLAG_B + COMM_MAX_BLOCKS * COMM_MAX_WORLD;     // [COMM_MAX_WORLD]  scalars posted
+constexpr int PAD_FLAG_D = PAD_FLAG_C + COMM_MAX_WORLD;                       // [COMM_MAX_WORLD]  Barzilai-Borwein rows posted
+constexpr int PAD_PAYLOAD = PAD_FLAG_D + COMM_MAX_WORLD;                      // [COMM_MAX_WORLD][4] floats: dual^2 part, primal part, #non-finite
+constexpr int PAD_BBROWS = PAD_PAYLOAD + 4 * COMM_MAX_WORLD;                  // [COMM_MAX_K][8] floats: six dots per worker
+constexpr int COMM_PAD_WORDS = 8192;
+static_assert(PAD_BBROWS + 8 * COMM_MAX_K <= COMM_PAD_WORDS, "control pad too small");
+
+// out record of an aggregation (floats): what the host reads back, once per round
+constexpr int OUT_DUAL_SQ = 0, OUT_PRIMAL = 1, OUT_NONFINITE = 2, OUT_STATUS = 3, OUT_RHO = 4, OUT_EPOCH = 5, OUT_TWO_SHOT = 6;
+constexpr int COMM_OUT_FLOATS = 8;
+// device scratch (floats): [0] dual^2, [1] #non-finite, [2] ticket (as uint), [4 + j] per-replica primal^2; self-cleaning
+constexpr int COMM_SCRATCH_FLOATS = 4 + COMM_MAX_LOCAL;
 
 struct CommArgs {
   int mode;                          // 0 FedAvg, 1 FedProx, 2 ADMM
   int K, n_local, world, rank;
   int n;                             // floats in the block slice
-  float inv_scale;                   // 1/K, or 1/(K rho) for ADMM
-  float rho;
+  int two_shot;                      // 1: rank r reduces slice r of the vector and broadcasts it (n_local == 1, world > 1)
+  int max_blocks;                    // grid cap (0 = one CTA per SM)
+  float rho;                         // penalty when rho_dev == nullptr
+  const float* rho_dev;              // device-resident penalty (adaptive ADMM): read by the kernel, never by the host
   const float* x[COMM_MAX_K];        // x_k slices of ALL workers (local or peer-mapped pointers)
   const float* y[COMM_MAX_K];        // y_k slices (ADMM) or nullptr
   float* xl[COMM_MAX_LOCAL];         // this process' replicas (writable aliases of the matching x[...])
   float* yl[COMM_MAX_LOCAL];
-  const float* mc_x;                 // multicast address of the x slice (NVLS path; requires K == world) or nullptr
-  const float* mc_y;
+  float* xw[COMM_MAX_WORLD];         // two-shot FedAvg: rank p's x slice (broadcast target over P2P)
+  float* zw[COMM_MAX_WORLD];         // two-shot FedProx / ADMM: rank p's z slice
+  float* mc_x;                       // multicast address of the x slice (NVLS: multimem.ld_reduce / multimem.st) or nullptr
+  float* mc_y;
+  float* mc_z;
   float* z;                          // local copy of the consensus vector (in/out)
-  float* out;                        // [0] dual^2, [1] primal (all workers), [2] #non-finite, [3] local primal, [4+j] per-replica sq
-  uint32_t* ctrl[COMM_MAX_WORLD];    // control pads of every rank (peer-mapped), 4 x COMM_MAX_WORLD words each
-  uint32_t* sync;                    // local: [0] = epoch of the last completed aggregation
+  float* out;                        // [COMM_OUT_FLOATS] result record
+  float* scratch;                    // [COMM_SCRATCH_FLOATS] device accumulators (zero between launches)
+  uint32_t* ctrl[COMM_MAX_WORLD];    // control pads of every rank (peer-mapped), COMM_PAD_WORDS words each
+  uint32_t* sync;                    // local: [0] = epoch of the last completed collective
+  long long timeout_cycles;          // per barrier; a timeout sets out[OUT_STATUS] = 100 + missing rank and lets the kernel end
 };
 void block_reduce_launch(const CommArgs& args, cudaStream_t s);
+
+// Barzilai-Borwein / spectral penalty update of consensus ADMM as ONE kernel: six dots per worker
+// straight from (x, y, yhat0, x0, z), rows exchanged through the control pads, the reference's sequential
+// accept/reject rule replayed identically on every rank, rho written to device memory, yhat0 / x0 carried forward.
+struct BBArgs {
+  int K, n_local, world, rank, n;
+  int seed_only;                     // 1: x0 <- x only (round 0)
+  int max_blocks;
+  float epsilon, alphacorrmin, rhomax;
+  const float* x[COMM_MAX_LOCAL];
+  const float* y[COMM_MAX_LOCAL];
+  float* yhat0[COMM_MAX_LOCAL];
+  float* x0[COMM_MAX_LOCAL];
+  int worker[COMM_MAX_LOCAL];        // global worker id of local replica j
+  const float* z;
+  float* rho_dev;                    // in/out: the shared penalty of this block
+  float* log;                        // [K][8]: d11, d12, d22, alpha, alphaSD, alphaMG, tested(0/1), rho after this worker's turn
+  float* scratch;                    // [8 * COMM_MAX_LOCAL + 8] zero between launches: dots + ticket + rho_turn
+  uint32_t* ctrl[COMM_MAX_WORLD];
+  uint32_t* sync;
+  float* out;                        // status goes to out[OUT_STATUS]
+  long long timeout_cycles;
+};
+constexpr int BB_SCRATCH_FLOATS = 8 * COMM_MAX_LOCAL + 8 + COMM_MAX_LOCAL;
+void bb_update_launch(const BBArgs& args, cudaStream_t s);
 
 }  // namespace fedb200

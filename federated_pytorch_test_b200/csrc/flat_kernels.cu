@@ -93,7 +93,10 @@ void bump_step(int* step_dev, cudaStream_t s) {
 __global__ void __launch_bounds__(256)
 adam_prox_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  const int* __restrict__ step_dev, int n, float lr, float b1, float b2, float eps,
-                 const float* __restrict__ z, const float* __restrict__ y, float rho, float l1, float l2) {
+                 const float* __restrict__ z, const float* __restrict__ y, float rho_host, float l1, float l2,
+                 const float* __restrict__ rho_dev) {
+  // adaptive ADMM keeps the penalty in device memory (written by bb_update_kernel): a captured graph never goes stale
+  const float rho = rho_dev != nullptr ? __ldg(rho_dev) : rho_host;
   const float t = static_cast<float>(*step_dev);
   const float bc1 = 1.f - powf(b1, t);
   const float bc2 = 1.f - powf(b2, t);
@@ -138,8 +141,9 @@ adam_prox_kernel(float* __restrict__ x, const float* __restrict__ g, float* __re
 }
 
 void adam_prox(float* x, const float* g, float* m, float* v, const int* step_dev, int n, float lr, float b1, float b2,
-               float eps, const float* z, const float* y, float rho, float l1, float l2, cudaStream_t s) {
-  adam_prox_kernel<<<grid_for(n), 256, 0, s>>>(x, g, m, v, step_dev, n, lr, b1, b2, eps, z, y, rho, l1, l2);
+               float eps, const float* z, const float* y, float rho, float l1, float l2, cudaStream_t s,
+               const float* rho_dev) {
+  adam_prox_kernel<<<grid_for(n), 256, 0, s>>>(x, g, m, v, step_dev, n, lr, b1, b2, eps, z, y, rho, l1, l2, rho_dev);
   check_launch("adam_prox");
 }
 

@@ -64,14 +64,15 @@ def _step_tensor(key, device) -> torch.Tensor:
     return t
 
 
-def adam_prox_step(x, g, m, v, step, lr, beta1, beta2, eps, z=None, y=None, rho=0.0, lambda1=0.0, lambda2=0.0) -> None:
+def adam_prox_step(x, g, m, v, step, lr, beta1, beta2, eps, z=None, y=None, rho=0.0, lambda1=0.0, lambda2=0.0,
+                   rho_dev=None) -> None:
     """``step`` is either a CUDA int32 tensor holding the (already incremented) step count
     (graph-capturable) or a Python int (copied into a per-buffer device counter)."""
     if not torch.is_tensor(step):
         t = _step_tensor(m.data_ptr(), x.device)
         t.fill_(int(step))
         step = t
-    ext().adam_prox(x, g, m, v, step, lr, beta1, beta2, eps, z, y, rho, lambda1, lambda2)
+    ext().adam_prox(x, g, m, v, step, lr, beta1, beta2, eps, z, y, rho, lambda1, lambda2, rho_dev)
 
 
 def bump_step(step: torch.Tensor) -> None:
@@ -176,45 +177,79 @@ def _stats_buffer(weight: torch.Tensor, C: int):
 
 
 def clear_caches() -> None:
-    """Drop cached derived tensors (call after loading a checkpoint into existing parameters)."""
-    _FLIP_CACHE.clear()
+    """Derived tensors must follow their source weights (call after loading a checkpoint into existing parameters).
+    Cached entries are refreshed IN PLACE: captured CUDA graphs hold their addresses."""
+    refresh_caches()
     _STATS_BUFFERS.clear()
-    _S2_CACHE.clear()
 
 
-def _flipped_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
-    """Rotated/transposed filter for the data gradient.  Frozen layers never change during a block visit (only the
-    active block is optimised or written back by FedAvg), so their flipped copy is computed once and reused; the
-    active block's is recomputed every step."""
+class _Derived:
+    """A derived filter (rotated / phase-packed) of a FROZEN layer, kept at a stable address and refreshed in place
+    whenever its source weights may have changed (``refresh_caches``: start of every block visit, checkpoint load)."""
+
+    __slots__ = ("src", "out", "fn")
+
+    def __init__(self, src, fn):
+        self.src, self.fn = src, fn
+        self.out = fn(src)
+
+    def refresh(self):
+        self.out.copy_(self.fn(self.src))
+
+
+def refresh_caches() -> int:
+    """Recompute every cached derived filter from its (possibly updated) source weights, in place.
+
+    Why: a layer is frozen while other blocks train, but its weights DO change when its own block is
+    visited (Adam + FedAvg write-back).  The first conv of a block needs no data gradient during its own visit, so its
+    cached rotated filter was never touched and went stale for all later visits of earlier blocks (Nloop >= 2) — and
+    CUDA graphs of those visits hold the cached tensor's address.  The engine calls this at the start of every block
+    visit; entries are never dropped, so graph-baked addresses stay valid."""
+    n = 0
+    with torch.no_grad():
+        for cache in (_FLIP_CACHE, _S2_CACHE):
+            for ent in cache.values():
+                ent.refresh()
+                n += 1
+    return n
+
+
+def _aliases(wk: torch.Tensor, weight: torch.Tensor) -> bool:
+    """True when the KRSC view ``wk`` aliases the parameter's own (persistent) storage.  Only such filters may be
+    cached by address: the NHWC copy of a plain NCHW parameter is a transient whose address the allocator recycles
+    (ADVICE r1, low)."""
+    return wk.untyped_storage().data_ptr() == weight.untyped_storage().data_ptr()
+
+
+def _derived(cache, wk: torch.Tensor, trainable: bool, fn, persistent: bool) -> torch.Tensor:
+    if trainable or not persistent:     # the active block's filters change every step: recompute, leave the cache alone
+        return fn(wk)
     key = (wk.data_ptr(), tuple(wk.shape))
-    if trainable:
-        _FLIP_CACHE.pop(key, None)
-        return ext().weight_flip(wk)
-    hit = _FLIP_CACHE.get(key)
-    if hit is None:
-        hit = ext().weight_flip(wk)
-        if not torch.cuda.is_current_stream_capturing():   # graph-pool memory must not escape its graph
-            _FLIP_CACHE[key] = hit
-    return hit
+    hit = cache.get(key)
+    if hit is not None:
+        return hit.out
+    if torch.cuda.is_current_stream_capturing():      # graph-pool memory must not escape its graph
+        return fn(wk)
+    ent = _Derived(wk, fn)
+    cache[key] = ent
+    return ent.out
+
+
+def _flipped_weight(wk: torch.Tensor, trainable: bool, persistent: bool = True) -> torch.Tensor:
+    """Rotated/transposed filter for the data gradient.  Frozen layers do not change during a block visit (only the
+    active block is optimised or written back by FedAvg), so their flipped copy is computed once per visit and reused;
+    the active block's is recomputed every step."""
+    return _derived(_FLIP_CACHE, wk, trainable, lambda w: ext().weight_flip(w), persistent)
 
 
 S2_DGRAD = os.environ.get("FEDB200_S2_DGRAD", "1") != "0"
 _S2_CACHE = {}
 
 
-def _packed_s2_weight(wk: torch.Tensor, trainable: bool) -> torch.Tensor:
+def _packed_s2_weight(wk: torch.Tensor, trainable: bool, persistent: bool = True) -> torch.Tensor:
     """Filter of the stride-1 convolution that computes a stride-2 data gradient (conv_math.py); cached for frozen
     layers exactly like the rotated filters above."""
-    key = (wk.data_ptr(), tuple(wk.shape))
-    if trainable:
-        _S2_CACHE.pop(key, None)
-        return conv_math.pack_dgrad_s2_weight(wk)
-    hit = _S2_CACHE.get(key)
-    if hit is None:
-        hit = conv_math.pack_dgrad_s2_weight(wk)
-        if not torch.cuda.is_current_stream_capturing():
-            _S2_CACHE[key] = hit
-    return hit
+    return _derived(_S2_CACHE, wk, trainable, conv_math.pack_dgrad_s2_weight, persistent)
 
 
 def _s2_dgrad_supported(e, xn: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, pad: int) -> bool:
@@ -227,9 +262,9 @@ def _s2_dgrad_supported(e, xn: torch.Tensor, dy: torch.Tensor, kh: int, kw: int,
     return bool(e.conv_supported(Ho, Wo, Co, 1))
 
 
-def _s2_dgrad(e, dy: torch.Tensor, wk: torch.Tensor, trainable: bool) -> torch.Tensor:
+def _s2_dgrad(e, dy: torch.Tensor, wk: torch.Tensor, trainable: bool, persistent: bool = True) -> torch.Tensor:
     """dx [N, 2Ho, 2Wo, Ci] of a stride-2 convolution: one stride-1 implicit GEMM over dy + a pixel shuffle."""
-    wp = _packed_s2_weight(wk, trainable)
+    wp = _packed_s2_weight(wk, trainable, persistent)
     if wk.shape[1] == 1:      # 1x1: only tap (0, 0) of the 2x2 window is populated -> run it as a 1x1 convolution
         w1 = wp[:, 0:1, 0:1, :].contiguous()
         return conv_math.dgrad_s2(dy, w1, lambda x, w: e.conv2d_nhwc(x, w, None, 1, 0, 1))
@@ -255,6 +290,7 @@ class _ConvBnAct(torch.autograd.Function):
         out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, res, running_mean, running_var, eps, momentum, act, self_clean)
         ctx.save_for_backward(xn, wk, y, out, mean, invstd, gamma, beta)
         ctx.cfg = (stride, pad, act, residual is not None, tuple(weight.shape), x.shape[1])
+        ctx.w_persistent = _aliases(wk, weight)
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -275,9 +311,9 @@ class _ConvBnAct(torch.autograd.Function):
             Ci = xn.shape[3]
             if stride == 1 and e.conv_supported(xn.shape[1], xn.shape[2], wshape[0], 1) and Ci % 4 == 0:
                 # data gradient of a stride-1 conv = conv of dy with the 180-degree rotated, transposed filter
-                dxn = e.conv2d_nhwc(dy, _flipped_weight(wk, need_w), None, 1, kh - 1 - pad, 1)
+                dxn = e.conv2d_nhwc(dy, _flipped_weight(wk, need_w, ctx.w_persistent), None, 1, kh - 1 - pad, 1)
             elif stride == 2 and _s2_dgrad_supported(e, xn, dy, kh, kw, pad):
-                dxn = _s2_dgrad(e, dy, wk, need_w)
+                dxn = _s2_dgrad(e, dy, wk, need_w, ctx.w_persistent)
             else:
                 dxn = torch.ops.aten.convolution_backward(
                     dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
@@ -319,6 +355,7 @@ class _ConvBnActSkip(torch.autograd.Function):
         out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, None, running_mean, running_var, eps, momentum, True, self_clean)
         ctx.save_for_backward(xn, wk, y, mean, invstd, gamma, beta)
         ctx.cfg = (stride, pad, tuple(weight.shape))
+        ctx.w_persistent = _aliases(wk, weight)
         return out.permute(0, 3, 1, 2), x.view_as(x)
 
     @staticmethod
@@ -333,7 +370,7 @@ class _ConvBnActSkip(torch.autograd.Function):
         kh = wshape[2]
         dx = dw = None
         if need_x:
-            wf = _flipped_weight(wk, need_w)
+            wf = _flipped_weight(wk, need_w, ctx.w_persistent)
             if dskip is not None:
                 acc = _nhwc(dskip)                       # the residual gradient of conv2's Function: ours alone
                 if not acc.is_contiguous():

@@ -132,7 +132,7 @@ def adam_prox_step(
     x: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int,
     lr: float, beta1: float, beta2: float, eps: float,
     z: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None, rho: float = 0.0,
-    lambda1: float = 0.0, lambda2: float = 0.0,
+    lambda1: float = 0.0, lambda2: float = 0.0, rho_dev: Optional[torch.Tensor] = None,
 ) -> None:
     """One Adam update of ``x`` with the penalty gradients added in closed form:
 
@@ -145,8 +145,10 @@ def adam_prox_step(
     if _cuda(x):
         from . import cuda_ops
 
-        cuda_ops.adam_prox_step(x, g, m, v, step, lr, beta1, beta2, eps, z, y, rho, lambda1, lambda2)
+        cuda_ops.adam_prox_step(x, g, m, v, step, lr, beta1, beta2, eps, z, y, rho, lambda1, lambda2, rho_dev)
         return
+    if rho_dev is not None:
+        rho = float(rho_dev)
     gt = penalty_grad(x, g, z, y, rho, lambda1, lambda2)
     m.mul_(beta1).add_(gt, alpha=1 - beta1)
     v.mul_(beta2).addcmul_(gt, gt, value=1 - beta2)

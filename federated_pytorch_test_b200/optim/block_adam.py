@@ -45,6 +45,7 @@ class BlockAdam(Optimizer):
         self.z: Optional[torch.Tensor] = None
         self.y: Optional[torch.Tensor] = None
         self.rho = 0.0
+        self.rho_dev: Optional[torch.Tensor] = None   # device-resident penalty (adaptive ADMM); wins over ``rho``
         self.lambda1 = 0.0
         self.lambda2 = 0.0
 
@@ -57,8 +58,9 @@ class BlockAdam(Optimizer):
     def g(self) -> torch.Tensor:
         return self.arena.grad[self._span[0]: self._span[1]]
 
-    def set_penalty(self, z=None, y=None, rho: float = 0.0, lambda1: float = 0.0, lambda2: float = 0.0) -> None:
+    def set_penalty(self, z=None, y=None, rho: float = 0.0, lambda1: float = 0.0, lambda2: float = 0.0, rho_dev=None) -> None:
         self.z, self.y, self.rho, self.lambda1, self.lambda2 = z, y, float(rho), float(lambda1), float(lambda2)
+        self.rho_dev = rho_dev
 
     def reset(self, lr: Optional[float] = None) -> None:
         """Back to the state of a freshly constructed optimizer (zero moments, step 0)."""
@@ -85,7 +87,7 @@ class BlockAdam(Optimizer):
             cuda_ops.bump_step(self.t_dev)
             step = self.t_dev
         flatops.adam_prox_step(self.x, self.g, self.m, self.v, step, grp["lr"], grp["betas"][0], grp["betas"][1],
-                               grp["eps"], self.z, self.y, self.rho, self.lambda1, self.lambda2)
+                               grp["eps"], self.z, self.y, self.rho, self.lambda1, self.lambda2, self.rho_dev)
 
     def step(self, closure: Optional[Callable] = None):
         loss = None
@@ -98,6 +100,8 @@ class BlockAdam(Optimizer):
     # -- stock-Adam compatible state ------------------------------------------
     def state_dict(self):
         base = self._span[0]
+        if self.t_dev is not None:      # graph replays only advance the device counter
+            self.t = max(self.t, int(self.t_dev.item()))
         for i in range(self.lo, self.hi + 1):
             p = self.arena.params[i]
             o = self.arena.offsets[i] - base

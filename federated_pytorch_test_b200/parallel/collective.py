@@ -100,8 +100,11 @@ class TorchCollective:
         return dual_sq, self.sum_scalars(local.reshape(1))[0]
 
     @torch.no_grad()
-    def admm_(self, xs: List[torch.Tensor], ys: List[torch.Tensor], z: torch.Tensor, rho: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    def admm_(self, xs: List[torch.Tensor], ys: List[torch.Tensor], z: torch.Tensor, rho: float,
+              rho_dev: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """z-update, dual ascent on every local ``y_k``; returns ``(dual_sq, primal)`` as :meth:`fedprox_`."""
+        if rho_dev is not None:
+            rho = float(rho_dev)
         contribs = [y + rho * x for x, y in zip(xs, ys)]
         znew = self.sum_blocks(contribs).div_(self.topo.K * rho)
         diff = z - znew
@@ -125,6 +128,46 @@ class TorchCollective:
             a, b, c = y - yh0, x - z, x - x0
             rows.append(flatops.multi_dot([(a, a), (a, b), (b, b), (a, c), (b, c), (c, c)]))
         return self.gather_rows(torch.stack(rows))
+
+    @torch.no_grad()
+    def bb_seed_(self, xs, x0s) -> None:
+        """Round 0 of a block visit: ``x0_k <- x_k`` (consensus_multi.py:244-246)."""
+        for x, x0 in zip(xs, x0s):
+            x0.copy_(x)
+
+    @torch.no_grad()
+    def bb_update_(self, xs, ys, yhat0s, x0s, z, rho: float, rho_dev: Optional[torch.Tensor], cfg) -> List[List[float]]:
+        """Barzilai-Borwein penalty update (consensus_multi.py:248-278): returns one row per worker
+        ``[d11, d12, d22, alpha, alphaSD, alphaMG, tested, rho after this worker's turn]``; ``yhat0``/``x0`` are carried
+        forward in place and ``rho_dev`` (if given) receives the final rho.  ATen/NCCL baseline + oracle of the kernel."""
+        import math
+
+        rows = self.bb_dots(xs, ys, yhat0s, x0s, z).double().cpu()
+        out, rho_at_turn = [], []
+        for ck in range(self.topo.K):
+            aa, ab, bb_, ac, bc, cc = (float(v) for v in rows[ck])
+            rho_at_turn.append(rho)
+            d11 = aa + 2.0 * rho * ab + rho * rho * bb_
+            d12 = ac + rho * bc
+            d22 = cc
+            alpha = aSD = aMG = 0.0
+            tested = 0.0
+            if abs(d12) > cfg.epsilon and d11 > cfg.epsilon and d22 > cfg.epsilon:
+                tested = 1.0
+                alpha = d12 / math.sqrt(d11 * d22)
+                aSD = d11 / d22
+                aMG = d12 / d22
+                ahat = aMG if 2.0 * aMG > aSD else aSD - 0.5 * aMG
+                if alpha >= cfg.alphacorrmin and ahat < cfg.rhomax:
+                    rho = ahat
+            out.append([d11, d12, d22, alpha, aSD, aMG, tested, rho])
+        # carry forward: yhat0_k <- y_k + rho_k (x_k - z) with the rho in force at worker k's turn
+        for i, ck in enumerate(self.topo.local_workers):
+            torch.add(ys[i], xs[i] - z, alpha=rho_at_turn[ck], out=yhat0s[i])
+            x0s[i].copy_(xs[i])
+        if rho_dev is not None:
+            rho_dev.fill_(rho)
+        return out
 
 
 def make_collective(topo: Topology, kind: str = "auto"):

@@ -3,12 +3,10 @@ straight out of peer memory over NVLink (``csrc/comm_kernels.cu``).  No NCCL on 
 
 Reference loops being replaced (Python loops over a dict of K modules): FedAvg mean + write-back + dual residual
 ``src/federated_multi.py:204-214``, FedProx mean + primal/dual residuals ``src/fedprox_multi.py:205-234``, ADMM z/y
-updates + residuals ``src/consensus_multi.py:226-299`` (Barzilai-Borwein dots ``:253-273`` go through
-``flatops.multi_dot``).
+updates + residuals ``src/consensus_multi.py:226-299``, Barzilai-Borwein penalty update ``:242-278``.
 
-Memory model: every replica's flat parameter arena (and, for
-ADMM, a same-shaped arena for the duals ``y``) is allocated from a
-:class:`SymmetricHeap`:
+Memory model: every replica's flat parameter arena (and same-shaped arenas for the
+consensus vector ``z`` and the ADMM duals ``y``) is allocated from a :class:`SymmetricHeap`:
 
 * ``world == 1``  — ordinary device memory (all K replicas are co-resident; the kernel
   just gets K local pointers — the reference's topology, but one launch instead of
@@ -19,13 +17,19 @@ ADMM, a same-shaped arena for the duals ``y``) is allocated from a
   ``torch.distributed`` is used for the handle exchange only.
 
 A block is a slice at the same offset of every arena, so the kernel needs nothing but
-K base pointers + one offset.  Cross-rank synchronisation is a flag barrier in a
+K base pointers + one offset.  Cross-rank synchronisation is a per-CTA flag barrier in a
 peer-mapped control pad (release/acquire at system scope, epoch counted in device
-memory), i.e. an aggregation round is host-free: one cooperative launch.
+memory); the penalty ``rho`` of adaptive ADMM, the epoch and all accumulators live in device
+memory, so an aggregation round is host-free and CUDA-graph capturable: one cooperative launch
+(+ one more for the Barzilai-Borwein update).  The host reads ONE 32-byte record per round.
+
+Small blocks are reduced ONE-SHOT (every rank pulls the whole vector: ``multimem.ld_reduce`` in the
+switch, or K P2P loads); blocks of 256 KB and more TWO-SHOT: rank r reduces slice r and broadcasts
+it with ``multimem.st`` (or P2P stores) into every rank's weights / consensus vector.
 """
 from __future__ import annotations
 
-import math
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -36,6 +40,19 @@ from .collective import TorchCollective
 from .topology import Topology
 
 _MAX_LOCAL = 16
+_OUT_FLOATS = 8
+_SCRATCH_FLOATS = 4 + _MAX_LOCAL
+_BB_SCRATCH_FLOATS = 8 * _MAX_LOCAL + 8 + _MAX_LOCAL
+_PAD_WORDS = 8192
+OUT_DUAL_SQ, OUT_PRIMAL, OUT_NONFINITE, OUT_STATUS, OUT_RHO, OUT_EPOCH, OUT_TWO_SHOT = range(7)
+
+TWO_SHOT_MIN_BYTES = int(os.environ.get("FEDB200_TWO_SHOT_BYTES", str(256 * 1024)))
+TWO_SHOT_MODE = os.environ.get("FEDB200_TWO_SHOT", "auto")          # 'auto' | '0' (never) | '1' (whenever legal)
+BARRIER_TIMEOUT_S = float(os.environ.get("FEDB200_BARRIER_TIMEOUT_S", "120"))
+
+
+class CollectiveTimeout(RuntimeError):
+    """A rank did not reach a cross-rank barrier of the aggregation kernel in time."""
 
 
 class SymmetricHeap:
@@ -106,27 +123,42 @@ class SymmetricHeap:
                 return a, p - a["base"]
         raise KeyError("tensor does not live in the symmetric heap")
 
+    def contains(self, t: torch.Tensor) -> bool:
+        try:
+            self.locate(t)
+            return True
+        except KeyError:
+            return False
+
 
 class FusedCollective(TorchCollective):
     name = "fused"
     fused = True
 
-    def __init__(self, topo: Topology):
+    def __init__(self, topo: Topology, heap=None, max_blocks: int = 0, timeout_s: Optional[float] = None):
         super().__init__(topo)
         if topo.device.type != "cuda":
             raise RuntimeError("FusedCollective needs a CUDA device")
         if topo.is_distributed and topo.K % topo.world_size != 0:
             raise RuntimeError("fused collectives need K to be a multiple of the number of ranks")
         self.ext = cuda_ops.ext()
-        self.heap = SymmetricHeap(topo)
+        self.heap = heap if heap is not None else SymmetricHeap(topo)
         dev = topo.device
-        self.out = torch.zeros(4 + _MAX_LOCAL, dtype=torch.float32, device=dev)
+        self.out = torch.zeros(_OUT_FLOATS, dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
+        self.bb_scratch = torch.zeros(_BB_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
+        self.bb_log = torch.zeros(8 * max(topo.K, 1), dtype=torch.float32, device=dev)
         self.sync = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.ctrl = self.heap.alloc(4 * 16, dtype=torch.int32)
-        self.ctrl_ptrs = list(self.heap.allocs[-1]["peer_ptrs"])
+        self.ctrl = self.heap.alloc(_PAD_WORDS, dtype=torch.int32)
+        self.ctrl_ptrs = list(self.heap.locate(self.ctrl)[0]["peer_ptrs"])
         self._aux: Dict[Tuple[int, str], torch.Tensor] = {}
-        self.use_multimem = True
+        self.use_multimem = os.environ.get("FEDB200_MULTIMEM", "1") != "0"
+        self.two_shot_mode = TWO_SHOT_MODE
+        self.max_blocks = int(max_blocks)
+        self.timeout_s = BARRIER_TIMEOUT_S if timeout_s is None else float(timeout_s)
         self.last_nonfinite = 0.0
+        self.last_two_shot = False
+        self.last_rho = float("nan")
 
     # -- arena hooks ------------------------------------------------------------
     def arena_allocator(self) -> Callable:
@@ -164,35 +196,89 @@ class FusedCollective(TorchCollective):
         local_idx = [rank + j * W for j in range(len(slices))]
         return ptrs, local_idx, mc
 
-    def _launch(self, mode: int, xs, ys, z, inv_scale: float, rho: float) -> torch.Tensor:
+    def _want_two_shot(self, mode: int, xs, z: torch.Tensor, n: int) -> bool:
+        W = self.topo.world_size
+        if W <= 1 or len(xs) != 1 or self.topo.K != W or self.two_shot_mode == "0":
+            return False
+        if mode != 0 and not self.heap.contains(z):
+            return False
+        return self.two_shot_mode == "1" or n * 4 >= TWO_SHOT_MIN_BYTES
+
+    def _launch(self, mode: int, xs, ys, z, rho: float, rho_dev=None) -> None:
         n = xs[0].numel()
         if any(t.numel() != n for t in xs) or z.numel() != n:
             raise ValueError("block slices must have equal length")
+        W = self.topo.world_size
         xp, local_idx, mcx = self._tables(xs)
         yp, mcy = [], 0
         if ys is not None:
             yp, _, mcy = self._tables(ys)
         if mode == 2 and not (mcx and mcy):
             mcx = mcy = 0
-        self.ext.block_reduce(mode, xp, yp, local_idx, z, n, inv_scale, rho, self.out, self.ctrl_ptrs, self.sync,
-                              self.topo.world_size, self.topo.rank, mcx, mcy)
+        two = self._want_two_shot(mode, xs, z, n)
+        mcz, xw, zw = 0, [], []
+        if two:
+            xw = [xp[r] for r in range(W)]
+            if mode != 0:
+                za, zoff = self.heap.locate(z)
+                zw = [za["peer_ptrs"][r] + zoff for r in range(W)]
+                if za["mc_ptr"] and self.use_multimem:
+                    mcz = za["mc_ptr"] + zoff
+        self.ext.block_reduce(mode, xp, yp, local_idx, z, n, float(rho), rho_dev, self.out, self.scratch, self.ctrl_ptrs,
+                              self.sync, W, self.topo.rank, mcx, mcy, mcz, xw, zw, bool(two), self.max_blocks,
+                              self.timeout_s)
         self.launches += 1
-        return self.out
+        self.last_two_shot = bool(two)
+
+    def read_record(self) -> List[float]:
+        """The ONE device->host read of a round: dual^2, primal, #non-finite, status, rho, epoch, two-shot flag."""
+        vals = self.out.tolist()
+        if vals[OUT_STATUS] != 0.0:
+            raise CollectiveTimeout("fedb200: rank %d timed out (%.0f s) waiting for rank %d in aggregation %d"
+                                    % (self.topo.rank, self.timeout_s, int(vals[OUT_STATUS]) - 100, int(vals[OUT_EPOCH])))
+        self.last_nonfinite = vals[OUT_NONFINITE]
+        self.last_rho = vals[OUT_RHO]
+        return vals
 
     # -- operators ----------------------------------------------------------------------
     @torch.no_grad()
     def fedavg_(self, xs, z, write_back: bool = True):
-        out = self._launch(0 if write_back else 1, xs, None, z, 1.0 / self.topo.K, 0.0)
-        return out[0].clone()
+        self._launch(0 if write_back else 1, xs, None, z, 0.0)
+        return self.read_record()[OUT_DUAL_SQ]
 
     @torch.no_grad()
     def fedprox_(self, xs, z, rho: float):
-        out = self._launch(1, xs, None, z, 1.0 / self.topo.K, rho)
-        res = out[:2].clone()
-        return res[0], res[1]
+        self._launch(1, xs, None, z, rho)
+        v = self.read_record()
+        return v[OUT_DUAL_SQ], v[OUT_PRIMAL]
 
     @torch.no_grad()
-    def admm_(self, xs, ys, z, rho: float):
-        out = self._launch(2, xs, ys, z, 1.0 / (self.topo.K * rho), rho)
-        res = out[:2].clone()
-        return res[0], res[1]
+    def admm_(self, xs, ys, z, rho: float, rho_dev=None):
+        self._launch(2, xs, ys, z, rho, rho_dev)
+        v = self.read_record()
+        return v[OUT_DUAL_SQ], v[OUT_PRIMAL]
+
+    # -- Barzilai-Borwein ---------------------------------------------------------------------
+    def _bb_launch(self, xs, ys, yhat0s, x0s, z, rho_dev, cfg, seed_only: bool) -> None:
+        W = self.topo.world_size
+        workers = [self.topo.rank + j * W for j in range(len(xs))]
+        self.ext.bb_update(list(xs), list(ys), list(yhat0s), list(x0s), z, workers, self.topo.K, rho_dev, self.bb_log,
+                           self.bb_scratch, self.out, self.ctrl_ptrs, self.sync, W, self.topo.rank,
+                           float(getattr(cfg, "epsilon", 1e-3)), float(getattr(cfg, "alphacorrmin", 0.2)),
+                           float(getattr(cfg, "rhomax", 0.1)), bool(seed_only), self.max_blocks, self.timeout_s)
+        self.launches += 1
+
+    @torch.no_grad()
+    def bb_seed_(self, xs, x0s) -> None:
+        dummy = xs[0]
+        rho = torch.zeros(1, dtype=torch.float32, device=dummy.device)
+        self._bb_launch(xs, [], [], x0s, dummy, rho, None, True)
+
+    @torch.no_grad()
+    def bb_update_(self, xs, ys, yhat0s, x0s, z, rho: float, rho_dev, cfg):
+        if rho_dev is None:
+            rho_dev = torch.full((1,), float(rho), dtype=torch.float32, device=z.device)
+        self._bb_launch(xs, ys, yhat0s, x0s, z, rho_dev, cfg, False)
+        # one read: the legacy log lines need the rows.  A barrier timeout is sticky in out[OUT_STATUS] and raised by the
+        # read_record() of the aggregation that always follows.
+        return self.bb_log[: 8 * self.topo.K].view(self.topo.K, 8).tolist()

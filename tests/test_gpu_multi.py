@@ -23,13 +23,13 @@ def _worker(rank, world, port, out_dir):
     report = {"transport": fused.heap.transport, "multicast": bool(fused.heap.allocs[-1]["mc_ptr"]), "cases": []}
     for use_mc in (True, False):
         fused.use_multimem = use_mc
-        for N in (456, 5130, 73984, 1180672):
+        for N in (456, 5130, 73984, 1180672, 3673088, 4720640):
             g = torch.Generator(device=dev).manual_seed(1000 * rank + N)
             arena = fused.heap.alloc(-(-N // 32) * 32)
             x = arena[:N]
             x.copy_(torch.randn(N, device=dev, generator=g))
             xr = x.clone()
-            z, zr = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+            z, zr = fused.zeros_like_block(x, "z"), torch.zeros(N, device=dev)     # symmetric z: two-shot broadcast target
             d1 = float(fused.fedavg_([x], z, True))
             d2 = float(base.fedavg_([xr], zr, True))
             ok = abs(d1 - d2) <= 1e-4 * abs(d2) + 1e-6 and torch.allclose(x, xr, rtol=1e-5, atol=1e-6) and torch.allclose(z, zr, rtol=1e-5, atol=1e-6)
@@ -45,7 +45,7 @@ def _worker(rank, world, port, out_dir):
             a = fused.fedprox_([x], z, 1.0)
             b = base.fedprox_([xr], zr, 1.0)
             ok = ok and abs(float(a[1]) - float(b[1])) <= 1e-3 * abs(float(b[1])) + 1e-6
-            report["cases"].append((use_mc, N, bool(ok)))
+            report["cases"].append((use_mc, N, bool(ok), bool(fused.last_two_shot)))
     torch.cuda.synchronize()
     if rank == 0:
         torch.save(report, os.path.join(out_dir, "report.pt"))
