@@ -40,7 +40,7 @@ from ..optim.block_adam import BlockAdam
 from ..optim.lbfgsnew import LBFGSNew
 from ..parallel.topology import Topology
 from ..utils.flat import FlatArena
-from ..utils.metrics import MetricsLog, PhaseTimers
+from ..utils.metrics import MetricsLog, PhaseTimers, nvtx_range
 from .strategies import Penalty, Strategy
 
 
@@ -135,6 +135,9 @@ class EngineConfig:
     aggregate_in_epoch_loop: bool = True    # reference: aggregation sits inside the epoch loop
     reset_optimizer_each_epoch: bool = False  # no_consensus_multi.py:129-132 recreates Adam every epoch (Q18)
     nan_guard: str = "raise"         # non-finite aggregation residual: 'raise' | 'warn' | 'off' 
+    resume_path: str = ""            # write a true-resume record here after every aggregation round ('' = never)
+    streams: bool = True             # co-resident replicas (K > #GPUs) step concurrently on their own CUDA streams
+    round_metrics: bool = True       # per-round JSONL: images/s, step / aggregate / eval device ms, bus GB/s
 
 
 class Engine:
@@ -160,6 +163,11 @@ class Engine:
         self.last_loss1: Optional[torch.Tensor] = None
         self.graph_replays = 0
         self.graph_kernel_launches = 0
+        self.aggregations_done = 0
+        self._resume_pos: Optional[Dict] = None       # set by ckpt.load_resume: schedule position to re-enter at
+        self._resume_state: Optional[Dict] = None
+        self._round_mark = {"images": 0, "t": time.perf_counter(), "ms": {}}
+        self._streams: Dict[int, "torch.cuda.Stream"] = {}
 
     # ------------------------------------------------------------------
     def log(self, msg: str, root_only: bool = False) -> None:
@@ -230,39 +238,140 @@ class Engine:
     def run(self) -> Dict:
         cfg, task, strat = self.cfg, self.task, self.strategy
         t0 = time.time()
-        for nloop in range(cfg.Nloop):
-            for visit in task.visits(nloop):
+        pos = self._resume_pos or {}
+        for nloop in range(int(pos.get("nloop", 0)), cfg.Nloop):
+            for vi, visit in enumerate(task.visits(nloop)):
                 if self.stop_requested:
                     break
-                self._run_visit(nloop, visit)
+                if self._resume_pos is not None and nloop == pos.get("nloop", 0) and vi < pos.get("visit", 0):
+                    continue                      # block visits completed before the checkpoint
+                self._run_visit(nloop, vi, visit)
             if self.stop_requested:
                 break
         self.log("Finished Training", root_only=True)
         return {"images_seen": self.images_seen, "steps": self.steps_done, "wall_s": time.time() - t0}
 
-    def _run_visit(self, nloop: int, visit: Visit) -> None:
+    def _refresh_derived(self) -> None:
+        """Derived filters cached by the kernels' autograd glue must follow the weights: weights of a
+        block change during ITS visit (Adam, FedAvg write-back) and are frozen again afterwards."""
+        if self.topo.device.type != "cuda":
+            return
+        from ..ops import functional as FX
+
+        if FX.fast_path_enabled():
+            from ..ops import cuda_ops
+
+            cuda_ops.refresh_caches()
+
+    def _run_visit(self, nloop: int, vi: int, visit: Visit) -> None:
         cfg, task, strat = self.cfg, self.task, self.strategy
         for rep in self.replicas:
             rep.set_trainable(visit)
+        self._refresh_derived()
         xs = [rep.block(visit) for rep in self.replicas]
         arena0 = self.replicas[0].arenas[visit.model]
         N = arena0.count(visit.lo, visit.hi)
         strat.begin_block(visit.ci, N, xs)
         self.optimizers = [self._make_optimizer(rep, visit) for rep in self.replicas]
-        for nadmm in range(cfg.Nadmm):
-            for epoch in range(cfg.Nepoch):
-                self.last_epoch = epoch
-                if cfg.reset_optimizer_each_epoch and epoch > 0:
-                    self.optimizers = [self._make_optimizer(rep, visit) for rep in self.replicas]
-                task.on_epoch_start(epoch, self)
-                for i_rep, rep in enumerate(self.replicas):
-                    self._run_shard(rep, self.optimizers[i_rep], visit, strat.penalty(i_rep), nloop, epoch, N)
-                    if self.stop_requested:
-                        return
-                if cfg.aggregate_in_epoch_loop:
-                    self._aggregate(visit, nloop, nadmm, epoch, N)
-            if not cfg.aggregate_in_epoch_loop:
-                self._aggregate(visit, nloop, nadmm, cfg.Nepoch - 1, N)
+        first_round = 0
+        if self._resume_pos is not None:          # re-enter the schedule inside this visit (true resume, SURVEY §5.4)
+            first_round = int(self._resume_pos.get("round", 0))
+            self._restore_visit_state()
+            self._resume_pos = None
+        rounds = [(nadmm, epoch) for nadmm in range(cfg.Nadmm) for epoch in range(cfg.Nepoch)]
+        for ri, (nadmm, epoch) in enumerate(rounds):
+            if ri < first_round:
+                continue
+            self.last_epoch = epoch
+            if cfg.reset_optimizer_each_epoch and epoch > 0:
+                self.optimizers = [self._make_optimizer(rep, visit) for rep in self.replicas]
+            task.on_epoch_start(epoch, self)
+            with nvtx_range("fedb200:steps"):
+                self._run_replicas(visit, nloop, epoch, N)
+            if self.stop_requested:
+                return
+            last_epoch_of_round = epoch == cfg.Nepoch - 1
+            if cfg.aggregate_in_epoch_loop or last_epoch_of_round:
+                self._aggregate(visit, nloop, nadmm, epoch if cfg.aggregate_in_epoch_loop else cfg.Nepoch - 1, N)
+                if cfg.resume_path:
+                    from ..utils import ckpt
+
+                    ckpt.save_resume(cfg.resume_path, self, dict(nloop=nloop, visit=vi, round=ri + 1, nadmm=nadmm, epoch=epoch))
+
+    def _restore_visit_state(self) -> None:
+        st = self._resume_state or {}
+        if st.get("strategy_state") and hasattr(self.strategy, "load_state"):
+            self.strategy.load_state(st["strategy_state"])
+        for rep, opt in zip(self.replicas, self.optimizers):
+            osd = (st.get("optimizers") or {}).get(rep.ck)
+            if osd is not None and hasattr(opt, "load_flat_state"):
+                opt.load_flat_state(osd)
+        self._resume_state = None
+
+    # ------------------------------------------------------------------
+    def _stream_of(self, i_rep: int):
+        stx = self._streams.get(i_rep)
+        if stx is None:
+            stx = torch.cuda.Stream(device=self.topo.device)
+            self._streams[i_rep] = stx
+        return stx
+
+    def _run_replicas(self, visit: Visit, nloop: int, epoch: int, N: int) -> None:
+        """One pass over the local replicas' shards.  One replica: plain loop.  Several co-resident replicas (K > #GPUs;
+        the reference's default K = 10): minibatch-major order with every replica on its own CUDA stream, so replica
+        j+1's kernels are queued while replica j's run and small layers of different replicas overlap on the SMs
+        (SURVEY §2.8).  Replicas are independent between aggregations, so the order does not change any result."""
+        cfg = self.cfg
+        reps = self.replicas
+        multi = (cfg.streams and len(reps) > 1 and self.topo.device.type == "cuda" and not cfg.be_verbose)
+        if not multi:
+            for i_rep, rep in enumerate(reps):
+                self._run_shard(rep, self.optimizers[i_rep], visit, self.strategy.penalty(i_rep), nloop, epoch, N)
+                if self.stop_requested:
+                    return
+            return
+        cur = torch.cuda.current_stream(self.topo.device)
+        iters = [iter(enumerate(self.task.batches(rep, visit, epoch))) for rep in reps]
+        pens = [self.strategy.penalty(i) for i in range(len(reps))]
+        running = [None] * len(reps)
+        live = list(range(len(reps)))
+        for i in live:
+            self._stream_of(i).wait_stream(cur)
+        while live and not self.stop_requested:
+            nxt = []
+            for i in live:
+                with torch.cuda.stream(self._stream_of(i)):       # the batch gather / H2D belongs to the replica's stream too
+                    try:
+                        bi, batch = next(iters[i])
+                    except StopIteration:
+                        continue
+                    if cfg.max_minibatches is not None and bi >= cfg.max_minibatches:
+                        continue
+                    running[i] = self._one_step(reps[i], self.optimizers[i], visit, batch, pens[i], running[i], bi, epoch, nloop, N)
+                nxt.append(i)
+                if self.stop_requested:
+                    break
+            live = nxt
+        for i in range(len(reps)):
+            cur.wait_stream(self._stream_of(i))
+        for i, rep in enumerate(reps):
+            rep.running_loss = float(running[i]) if running[i] is not None else 0.0
+
+    def _one_step(self, rep: Replica, opt, visit: Visit, batch, pen: Penalty, running, i: int, epoch: int, nloop: int, N: int):
+        cfg, task = self.cfg, self.task
+        with self.timers.phase("step"):
+            if cfg.graphs and isinstance(opt, BlockAdam) and rep.device.type == "cuda":
+                loss1 = self._graphed_step(rep, opt, visit, batch, pen)
+            else:
+                loss1 = self._train_step(rep, opt, visit, batch, pen)
+        running = loss1 if running is None else running + loss1
+        self.last_loss1 = loss1
+        self.images_seen += task.batch_size_of(batch)
+        self.steps_done += 1
+        task.after_minibatch(rep, visit, batch, i, epoch, nloop, N, loss1, self)
+        if self.step_hook is not None:
+            self.step_hook(self)
+        return running
 
     def _run_shard(self, rep: Replica, opt, visit: Visit, pen: Penalty, nloop: int, epoch: int, N: int) -> None:
         cfg, task = self.cfg, self.task
@@ -270,35 +379,57 @@ class Engine:
         for i, batch in enumerate(task.batches(rep, visit, epoch)):
             if cfg.max_minibatches is not None and i >= cfg.max_minibatches:
                 break
-            with self.timers.phase("step"):
-                if cfg.graphs and isinstance(opt, BlockAdam) and rep.device.type == "cuda":
-                    loss1 = self._graphed_step(rep, opt, visit, batch, pen)
-                else:
-                    loss1 = self._train_step(rep, opt, visit, batch, pen)
-            running = loss1 if running is None else running + loss1
-            self.last_loss1 = loss1
-            self.images_seen += task.batch_size_of(batch)
-            self.steps_done += 1
-            task.after_minibatch(rep, visit, batch, i, epoch, nloop, N, loss1, self)
-            if self.step_hook is not None:
-                self.step_hook(self)
-                if self.stop_requested:
-                    break
+            running = self._one_step(rep, opt, visit, batch, pen, running, i, epoch, nloop, N)
+            if self.stop_requested:
+                break
         rep.running_loss = float(running) if running is not None else 0.0
 
     def _aggregate(self, visit: Visit, nloop: int, nadmm: int, epoch: int, N: int) -> None:
-        with self.timers.phase("aggregate"):
+        with nvtx_range("fedb200:aggregate"), self.timers.phase("aggregate"):
             metrics = self.strategy.aggregate(nadmm)
+        self.aggregations_done += 1
         ctx = {"nloop": nloop, "nadmm": nadmm, "epoch": epoch, "N": N, "rho_mean": self.strategy.rho_mean()}
+        if metrics is not None and getattr(self.coll, "last_nonfinite", 0.0):
+            metrics["nonfinite"] = float(self.coll.last_nonfinite)      # counted inside the aggregation kernel
         self._check_finite(visit, metrics, ctx)
+        acc = None
+        if self.cfg.check_results:
+            with nvtx_range("fedb200:eval"), self.timers.phase("eval"):
+                acc = self.task.evaluate(self.replicas, self)
         if metrics:
             self.task.aggregate_log(visit, metrics, ctx, self)
-            self.metrics.write(dict(kind="round", block=visit.ci, label=list(visit.label), model=visit.model, **ctx, **metrics))
-        if self.cfg.check_results:
-            with self.timers.phase("eval"):
-                acc = self.task.evaluate(self.replicas, self)
-            if acc is not None:
-                self.metrics.write(dict(kind="eval", block=visit.ci, **ctx, accuracy=acc))
+            row = dict(kind="round", block=visit.ci, label=list(visit.label), model=visit.model, **ctx, **metrics)
+            if self.cfg.round_metrics:
+                row.update(self._round_perf(N))
+            self.metrics.write(row)
+        if acc is not None:
+            self.metrics.write(dict(kind="eval", block=visit.ci, **ctx, accuracy=acc))
+
+    def _round_perf(self, N: int) -> Dict[str, float]:
+        """Throughput and device-time fields of the round that just ended: images/s of this process,
+        device ms per phase (CUDA events, resolved lazily: the round's own host read has already synchronised),
+        aggregation latency and NVLink bus bandwidth (nccl-tests convention: 2 (W-1)/W * bytes / time)."""
+        now = time.perf_counter()
+        mark = self._round_mark
+        summ = self.timers.summary(reduce_max=False)
+        out: Dict[str, float] = {}
+        dt = max(now - mark["t"], 1e-9)
+        out["images_per_s"] = (self.images_seen - mark["images"]) / dt
+        for k, v in summ.items():
+            prev = mark["ms"].get(k, {"ms": 0.0, "count": 0})
+            d_ms, d_n = v["ms"] - prev["ms"], v["count"] - prev["count"]
+            if d_n > 0:
+                out[k + "_ms"] = d_ms
+                out[k + "_count"] = d_n
+        agg_ms = out.get("aggregate_ms")
+        if agg_ms:
+            out["aggregate_us"] = 1e3 * agg_ms / max(out.get("aggregate_count", 1), 1)
+            W = max(self.topo.world_size, 1)
+            if W > 1:
+                out["bus_GBs"] = 2.0 * (W - 1) / W * 4.0 * N / (out["aggregate_us"] * 1e-6) / 1e9
+        out["two_shot"] = bool(getattr(self.coll, "last_two_shot", False))
+        self._round_mark = {"images": self.images_seen, "t": now, "ms": {k: dict(v) for k, v in summ.items()}}
+        return out
 
     def _check_finite(self, visit: Visit, metrics: Optional[Dict[str, float]], ctx: Dict) -> None:
         """Failure detection: the residuals are norms over the REDUCED vector of every worker, so one
@@ -306,6 +437,8 @@ class Engine:
         if not metrics or self.cfg.nan_guard == "off":
             return
         bad = [k for k in ("dual", "primal") if k in metrics and not math.isfinite(float(metrics[k]))]
+        if not bad and metrics.get("nonfinite"):
+            bad = ["reduced vector (%d non-finite entries)" % int(metrics["nonfinite"])]
         if not bad:
             return
         msg = ("non-finite %s residual after aggregating block %s (ids %s) at loop %d, round %d, epoch %d on rank %d: "

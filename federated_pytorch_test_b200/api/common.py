@@ -48,7 +48,8 @@ def setup_runtime(cfg: CommonConfig) -> Tuple[Topology, object]:
 def engine_config(cfg: CommonConfig, **kw) -> EngineConfig:
     base = dict(Nloop=cfg.Nloop, Nadmm=cfg.Nadmm, Nepoch=cfg.Nepoch, check_results=cfg.check_results,
                 be_verbose=cfg.be_verbose, diagnostics=cfg.diagnostics, graphs=cfg.graphs,
-                max_minibatches=cfg.max_minibatches or None, nan_guard=getattr(cfg, "nan_guard", "raise"))
+                max_minibatches=cfg.max_minibatches or None, nan_guard=getattr(cfg, "nan_guard", "raise"),
+                resume_path=getattr(cfg, "resume_out", ""), streams=getattr(cfg, "streams", True))
     base.update(kw)
     return EngineConfig(**base)
 

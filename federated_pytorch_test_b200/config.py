@@ -54,7 +54,9 @@ class CommonConfig:
     ckpt_dir: str = "."
     metrics_path: str = ""
     max_minibatches: int = 0        # >0 caps minibatches per round (smoke tests / benchmarks)
-    resume: str = ""                # path of a true-resume record written by this framework
+    resume: str = ""                # path of a true-resume record written by this framework: re-enter the schedule there
+    resume_out: str = ""            # write the true-resume record here after every aggregation round ('' = never)
+    streams: bool = True            # co-resident replicas (K > #GPUs) step concurrently on their own CUDA streams
 
 
 @dataclass

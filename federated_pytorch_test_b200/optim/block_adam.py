@@ -97,6 +97,20 @@ class BlockAdam(Optimizer):
         self.apply_update()
         return loss
 
+    # -- true resume (utils/ckpt.py) ----------------------------------------------
+    def flat_state(self) -> dict:
+        t = int(self.t_dev.item()) if self.t_dev is not None else self.t
+        return {"m": self.m.detach().cpu().clone(), "v": self.v.detach().cpu().clone(), "t": max(t, self.t),
+                "lr": self.param_groups[0]["lr"]}
+
+    def load_flat_state(self, rec: dict) -> None:
+        self.m.copy_(rec["m"].to(self.m.device))
+        self.v.copy_(rec["v"].to(self.v.device))
+        self.t = int(rec["t"])
+        if self.t_dev is not None:
+            self.t_dev.fill_(self.t)
+        self.param_groups[0]["lr"] = rec.get("lr", self.param_groups[0]["lr"])
+
     # -- stock-Adam compatible state ------------------------------------------
     def state_dict(self):
         base = self._span[0]

@@ -525,6 +525,36 @@ class LBFGSNew(Optimizer):
             state["running_avg"], state["running_avg_sq"] = run_mean, run_m2
         return orig_loss
 
+    # -- true resume (utils/ckpt.py): everything step() carries between calls, as plain CPU tensors ----------------
+    def flat_state(self) -> dict:
+        st = self.state[self._params[0]]
+        hist = st.get("_hist")
+        out = {k: st.get(k) for k in ("func_evals", "n_iter", "t", "H_diag", "prev_loss")}
+        for k in ("d", "prev_flat_grad", "running_avg", "running_avg_sq"):
+            v = st.get(k)
+            out[k] = v.detach().cpu().clone() if torch.is_tensor(v) else None
+        if hist is not None:
+            out["hist_Y"] = torch.stack([y.detach().cpu() for y in hist.dirs()]) if len(hist) else None
+            out["hist_S"] = torch.stack([x.detach().cpu() for x in hist.steps()]) if len(hist) else None
+            out["hist_m"] = hist.m
+        return out
+
+    def load_flat_state(self, rec: dict) -> None:
+        st = self.state[self._params[0]]
+        dev = self._params[0].device
+        for k in ("func_evals", "n_iter", "t", "H_diag", "prev_loss"):
+            if rec.get(k) is not None:
+                st[k] = rec[k]
+        for k in ("d", "prev_flat_grad", "running_avg", "running_avg_sq"):
+            if rec.get(k) is not None:
+                st[k] = rec[k].to(dev)
+        if rec.get("hist_m") is not None and st.get("d") is not None:
+            hist = flatops.PairHistory(int(rec["hist_m"]), st["d"])
+            if rec.get("hist_Y") is not None:
+                for y, x in zip(rec["hist_Y"], rec["hist_S"]):
+                    hist.push(y.to(dev), x.to(dev))
+            st["_hist"] = hist
+
     def state_dict(self):
         sd = super().state_dict()
         # the ring-buffer object is an implementation detail; ``old_dirs``/``old_stps`` carry the data

@@ -77,7 +77,11 @@ def load_model_only(path: str, net: nn.Module, device) -> None:
 
 # ----------------------------------------------------------------------------
 def save_resume(path: str, engine, position: Dict) -> str:
-    """True resume record: schedule position + consensus state + per-replica weights/optimizers + RNG."""
+    """True resume record, written by the engine after every aggregation round when
+    ``EngineConfig.resume_path`` is set: schedule position ``(nloop, visit, round)`` = where to RE-ENTER, consensus
+    state of the open block visit (z, y_k, rho table, BB vectors), per-replica weights + BatchNorm buffers, the
+    optimizers' flat state (Adam moments + step / L-BFGS history, direction, Welford statistics), loader RNG streams,
+    global RNG states and the run counters.  Written atomically (tmp + rename); one file per rank."""
     strat_state = {}
     for k, v in engine.strategy.state().items():
         if torch.is_tensor(v):
@@ -86,6 +90,13 @@ def save_resume(path: str, engine, position: Dict) -> str:
             strat_state[k] = [t.detach().cpu().clone() for t in v]
         else:
             strat_state[k] = v
+    opts = {}
+    for rep, opt in zip(engine.replicas, engine.optimizers or []):
+        opts[rep.ck] = opt.flat_state() if hasattr(opt, "flat_state") else None
+    loaders = {}
+    for ck, ld in getattr(engine.task, "_loaders", {}).items():
+        if hasattr(ld, "gen"):
+            loaders[ck] = ld.gen.get_state()
     rec = {
         "position": dict(position),
         "strategy": engine.strategy.name,
@@ -94,22 +105,30 @@ def save_resume(path: str, engine, position: Dict) -> str:
         "replicas": {
             rep.ck: {key: dense_state_dict(net) for key, net in rep.nets.items()} for rep in engine.replicas
         },
-        "optimizers": {
-            rep.ck: opt.state_dict() for rep, opt in zip(engine.replicas, engine.optimizers)
-        } if engine.optimizers else {},
+        "optimizers": opts,
+        "loader_rng": loaders,
+        "counters": {"images_seen": engine.images_seen, "steps_done": engine.steps_done,
+                     "aggregations_done": getattr(engine, "aggregations_done", 0)},
         "rng": {"torch": torch.get_rng_state(),
                 "cuda": torch.cuda.get_rng_state_all() if torch.cuda.is_available() else None},
     }
     if engine.topo.is_distributed:
         path = "%s.rank%d" % (path, engine.topo.rank)
-    torch.save(rec, path)
+    tmp = path + ".tmp"
+    torch.save(rec, tmp)
+    os.replace(tmp, path)
     return path
 
 
 def load_resume(path: str, engine) -> Dict:
+    """Restore a record written by :func:`save_resume` and arm the engine to re-enter the schedule at the recorded
+    position: weights now; consensus / optimizer state when the engine reaches the recorded block visit (the buffers
+    only exist then)."""
     if engine.topo.is_distributed:
         path = "%s.rank%d" % (path, engine.topo.rank)
     rec = torch.load(path, map_location="cpu", weights_only=False)
+    if rec.get("strategy") not in (None, engine.strategy.name):
+        raise ValueError("resume record was written by strategy %r, this run uses %r" % (rec.get("strategy"), engine.strategy.name))
     for rep in engine.replicas:
         for key, net in rep.nets.items():
             load_into(net, rec["replicas"][rep.ck][key])
@@ -119,4 +138,14 @@ def load_resume(path: str, engine) -> Dict:
             torch.cuda.set_rng_state_all(rec["rng"]["cuda"])
         except Exception:
             pass
+    for ck, state in (rec.get("loader_rng") or {}).items():
+        ld = engine.task.loader(ck) if hasattr(engine.task, "loader") else None
+        if ld is not None and hasattr(ld, "gen"):
+            ld.gen.set_state(state)
+    cnt = rec.get("counters") or {}
+    engine.images_seen = int(cnt.get("images_seen", 0))
+    engine.steps_done = int(cnt.get("steps_done", 0))
+    engine.aggregations_done = int(cnt.get("aggregations_done", 0))
+    engine._resume_pos = dict(rec["position"])
+    engine._resume_state = {"strategy_state": rec.get("strategy_state"), "optimizers": rec.get("optimizers")}
     return rec

@@ -252,3 +252,47 @@ def test_co_resident_replicas_over_two_ranks_match_single_process(tmp_path, algo
     assert len(a) == len(b) == 10
     for x, y in zip(a, b):
         assert float(x.rsplit("=", 1)[1]) == pytest.approx(float(y.rsplit("=", 1)[1]), rel=1e-3, abs=1e-9), (x, y)
+
+
+# ------------------------------------------------------------------------------------------ true resume
+class _Killed(Exception):
+    pass
+
+
+@pytest.mark.parametrize("mod,extra", [(fedprox_multi, {}), (consensus_multi, {"bb_update": True}), (federated_multi, {})])
+def test_kill_and_resume_reproduces_the_trace(tmp_path, mod, extra):
+    """Run A: uninterrupted.  Run B: killed mid-schedule (inside a block visit, between two rounds), then a NEW process
+    state (fresh engine) resumes from the record the engine wrote after the last completed round.  The residual traces
+    of B-before + B-after must equal A line by line: schedule position, z / y / rho / BB vectors, Adam moments + step
+    count, loader RNG and global RNG all re-enter exactly."""
+    from federated_pytorch_test_b200.algo.engine import Engine
+
+    kw = dict(K=2, Nloop=1, Nadmm=3, max_minibatches=2, check_results=False, use_cuda=False, **extra)
+    key = "dual (" if mod is federated_multi else "block=["
+    _, full = _run(mod, **kw)
+    full = [l for l in full if l.startswith(key)]
+    assert len(full) == 15
+
+    rec = str(tmp_path / "resume.pt")
+    kill_at = 2 * 2 * (3 + 2) - 1          # a step inside round 2 of the second block visit (7 rounds completed before it... )
+    orig_init = Engine.__init__
+
+    def patched(self, *a, **k):
+        orig_init(self, *a, **k)
+
+        def hook(e):
+            if e.steps_done == kill_at:
+                raise _Killed()
+        self.step_hook = hook
+    Engine.__init__ = patched
+    first = []
+    try:
+        with pytest.raises(_Killed):
+            mod.run(mod.Config(**{**TINY, **kw, "resume_out": rec}), log=first.append)
+    finally:
+        Engine.__init__ = orig_init
+    first = [l for l in first if l.startswith(key)]
+    assert 0 < len(first) < 15 and os.path.exists(rec)
+    _, second = _run(mod, **kw, resume=rec)
+    second = [l for l in second if l.startswith(key)]
+    assert first + second == full

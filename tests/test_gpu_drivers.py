@@ -85,13 +85,13 @@ def test_federated_multi_fused_equals_torch_collective():
 def test_true_resume_record_roundtrip(tmp_path):
     from federated_pytorch_test_b200.utils import ckpt
     eng, _ = _run(consensus_multi, K=2, Nloop=1, Nadmm=1, max_minibatches=1, check_results=False, model="Net", graphs=False)
-    path = ckpt.save_resume(str(tmp_path / "resume.pt"), eng, {"nloop": 0, "ci": 4, "nadmm": 0})
+    path = ckpt.save_resume(str(tmp_path / "resume.pt"), eng, {"nloop": 0, "visit": 4, "round": 1})
     arena = eng.replicas[0].arenas["net"]
     before = arena.data.clone()
     with torch.no_grad():
         for p in eng.replicas[0].nets["net"].parameters():   # perturb parameters only: alignment gaps must stay zero
             p.add_(1.0)
     rec = ckpt.load_resume(str(tmp_path / "resume.pt"), eng)
-    assert rec["position"]["ci"] == 4 and rec["strategy"] == "admm" and "rho" in rec["strategy_state"]
+    assert rec["position"]["visit"] == 4 and rec["strategy"] == "admm" and "rho" in rec["strategy_state"]
     torch.testing.assert_close(arena.data, before)
     assert os.path.exists(path)
