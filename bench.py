@@ -224,7 +224,14 @@ def run_ours(args) -> dict:
     pending = []
     sampler = {"d": ClockSampler(dev.index or 0) if topo.is_root else None, "e": ClockSampler(dev.index or 0) if topo.is_root else None}
 
+    import gc
+
+    gc.collect()
+    gc.freeze()           # everything built so far is long-lived: keep it out of the collector's generations
+
     def open_window(tag, ev):
+        gc.collect()
+        gc.disable()      # a cyclic-GC pause (~10 ms with this heap) inside a 50 ms window is 20 % noise; re-enabled at close
         topo.barrier()
         torch.cuda.synchronize(dev)
         if sampler[tag]:
@@ -238,6 +245,7 @@ def run_ours(args) -> dict:
         ev.record()
         torch.cuda.synchronize(dev)
         topo.barrier()
+        gc.enable()
         s = st[tag]
         s["t1"] = time.perf_counter()
         s["launches"] = (cuda_ops.launch_count() - s["l0"]) + (getattr(eng, "graph_kernel_launches", 0) - s["g0"])

@@ -60,6 +60,20 @@ class Visit:
     tag: Dict = field(default_factory=dict)
 
 
+
+def _grad_sink():
+    """Weight-gradient kernels may accumulate straight into the arena's gradient views during these backward calls."""
+    from ..ops import functional as FX
+
+    if torch.cuda.is_available() and FX.fast_path_enabled():
+        from ..ops import cuda_ops
+
+        return cuda_ops.accumulate_into_grad()
+    import contextlib
+
+    return contextlib.nullcontext()
+
+
 class Replica:
     """One logical worker: its models, arenas and data."""
 
@@ -152,6 +166,8 @@ class Engine:
         for rep in self.replicas:
             for arena in rep.arenas.values():
                 collective.register_arena(arena)
+        if hasattr(collective, "warmup"):
+            collective.warmup()          # lazy CUDA initialisation of the aggregation kernels belongs here, not in round 0
         self.optimizers: List = []
         self.images_seen = 0
         self.steps_done = 0
@@ -203,7 +219,8 @@ class Engine:
             def closure():
                 opt.zero_grad()
                 loss = task.loss(rep, batch)
-                loss.backward()
+                with _grad_sink():
+                    loss.backward()
                 pre_loss[0] = loss.detach()
                 return loss
 
@@ -218,7 +235,8 @@ class Engine:
                     opt.zero_grad()
                 loss = task.loss(rep, batch)
                 if loss.requires_grad:
-                    loss.backward()
+                    with _grad_sink():
+                        loss.backward()
                     if has_pen:
                         flatops.add_penalty_grad_(g, x, pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2)
                 total = loss.detach()

@@ -25,6 +25,20 @@ from ..ops import cuda_ops
 from ..optim.block_adam import BlockAdam
 
 
+
+def _grad_sink():
+    """Weight-gradient kernels may accumulate straight into the arena's gradient views during these backward calls."""
+    from ..ops import functional as FX
+
+    if torch.cuda.is_available() and FX.fast_path_enabled():
+        from ..ops import cuda_ops
+
+        return cuda_ops.accumulate_into_grad()
+    import contextlib
+
+    return contextlib.nullcontext()
+
+
 class GraphedAdamStep:
     WARMUP = 3
 
@@ -43,7 +57,8 @@ class GraphedAdamStep:
         task, rep, opt = self.engine.task, self.rep, self.opt
         opt.zero_grad()
         loss = task.loss(rep, self.static)
-        loss.backward()
+        with _grad_sink():
+            loss.backward()
         opt.apply_update()
         if self.engine.cfg.diagnostics == "post":
             with torch.no_grad():
@@ -57,11 +72,23 @@ class GraphedAdamStep:
                 rho_key, self.visit.lambda1, self.visit.lambda2)
 
     def _capture(self) -> None:
+        import gc
+
         before = cuda_ops.launch_count()
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=self.stream):
-            self.loss_out = self._body()
+        # A CUDAGraph that is garbage (e.g. the graphs of a previous Engine, kept alive by a reference cycle) must not be
+        # finalised while a capture is in progress: cudaGraphExecDestroy is "not permitted when stream is capturing" and
+        # invalidates the capture (measured: profiles/r2_call2).  torch.cuda.graph no longer collects by itself.
+        gc.collect()
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, stream=self.stream):
+                self.loss_out = self._body()
+        finally:
+            if was_enabled:
+                gc.enable()
         self.graph = g
         self.kernels_per_replay = cuda_ops.launch_count() - before
 

@@ -171,16 +171,24 @@ class ClassifierTask(Task):
         under ``no_grad`` (no numerical effect).  Counting stays on the device; one
         read per replica.
         """
-        accs = []
+        fused = self.topo.device.type == "cuda" and FX.fast_path_enabled()
+        counters = []
         for rep in reps:
             net = rep.nets["net"]
-            correct = torch.zeros((), dtype=torch.int64, device=rep.device)
-            total = 0
+            counter = torch.zeros(2, dtype=torch.int64, device=rep.device)      # [#correct, #seen], stays on the device
             for x, y in self.test_loader(rep.ck):
-                pred = net(x).argmax(dim=1)
-                correct += (pred == y).sum()
-                total += y.shape[0]
-            c = int(correct)
+                logits = net(x)
+                if fused:
+                    from ..ops import cuda_ops
+
+                    cuda_ops.argmax_count(logits, y, counter)                    # argmax + compare + count: one kernel (G21)
+                else:
+                    counter[0] += (logits.argmax(dim=1) == y).sum()
+                    counter[1] += y.shape[0]
+            counters.append(counter)
+        accs = []
+        for rep, counter in zip(reps, counters):                                 # ONE read per replica, after all forwards are queued
+            c, total = (int(v) for v in counter.tolist())
             engine.log(legacy_log.accuracy_line(rep.ck, total, c))
             accs.append(legacy_log.accuracy_exact(c, total))
         return accs

@@ -242,6 +242,23 @@ Tensor conv2d_nhwc_sized(Tensor x, Tensor w, c10::optional<Tensor> stats, int64_
   return y;
 }
 
+// Weight gradient: dw [Co, kh, kw, Cw] += wgrad(x [N,H,W,Cx], dy [N,Ho,Wo,Co]).  `dw` is accumulated into (zeroed by the
+// caller, or the parameter's gradient buffer itself); Cw <= Cx (channel-padded activations).
+bool conv_wgrad_supported(int64_t Cx, int64_t Co, int64_t stride, int64_t Wo, int64_t Ho) {
+  return fb::conv_wgrad_supported((int)Cx, (int)Co, (int)stride, (int)Wo, (int)Ho);
+}
+void conv_wgrad(Tensor x, Tensor dy, Tensor dw, int64_t stride, int64_t pad, int64_t dil) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(dy); CHECK_F32_CUDA(dw); CHECK_CONTIG(x); CHECK_CONTIG(dy); CHECK_CONTIG(dw);
+  TORCH_CHECK(x.dim() == 4 && dy.dim() == 4 && dw.dim() == 4 && x.size(0) == dy.size(0) && dw.size(0) == dy.size(3) &&
+              dw.size(3) <= x.size(3), "conv_wgrad: x [N,H,W,Cx], dy [N,Ho,Wo,Co], dw [Co,kh,kw,Cw<=Cx]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), Cx = (int)x.size(3);
+  const int Ho = (int)dy.size(1), Wo = (int)dy.size(2), Co = (int)dy.size(3);
+  const int kh = (int)dw.size(1), kw = (int)dw.size(2), Cw = (int)dw.size(3);
+  fb::conv_wgrad_tf32(fptr(x), fptr(dy), fptr_mut(dw), NB, H, W, Cx, Cw, Co, kh, kw, (int)stride, (int)pad, (int)dil, Ho, Wo,
+                      cur_stream());
+}
+
 // y += conv(x, w), in place (experimental)
 Tensor conv2d_nhwc_accumulate(Tensor x, Tensor w, Tensor y, int64_t stride, int64_t pad, int64_t dil) {
   CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_F32_CUDA(y); CHECK_CONTIG(x); CHECK_CONTIG(w); CHECK_CONTIG(y);
@@ -307,6 +324,149 @@ std::vector<Tensor> vae_loss_bwd(Tensor recon, Tensor x, Tensor mu, Tensor logva
   fb::vae_loss_bwd(fptr(recon), fptr(x), (int)recon.numel(), fptr(mu), fptr(logvar), (int)mu.numel(), fptr(g), fptr_mut(dr),
                    fptr_mut(dm), fptr_mut(dl), cur_stream());
   return {dr, dm, dl};
+}
+
+// ---------------------------------------------------------------------------------------------- aux (true fp32)
+// out[M,N] (+)= act(x[M,K] w[N,K]^T + b): nn.Linear forward
+Tensor linear_f32(Tensor x, Tensor w, c10::optional<Tensor> bias, bool act) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1), "linear_f32: x [M,K], w [N,K]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int M = (int)x.size(0), K = (int)x.size(1), N = (int)w.size(0);
+  auto out = torch::empty({M, N}, x.options());
+  fb::gemm_f32(fptr(x), fptr(w), opt_ptr(bias), fptr_mut(out), M, N, K, K, 1, 1, K, N, act ? 1 : 0, 0, cur_stream());
+  return out;
+}
+// dx[M,K] = dz[M,N] w[N,K]
+Tensor linear_f32_dgrad(Tensor dz, Tensor w) {
+  CHECK_F32_CUDA(dz); CHECK_F32_CUDA(w); CHECK_CONTIG(dz); CHECK_CONTIG(w);
+  c10::cuda::CUDAGuard guard(dz.device());
+  const int M = (int)dz.size(0), N = (int)dz.size(1), K = (int)w.size(1);
+  auto dx = torch::empty({M, K}, dz.options());
+  fb::gemm_f32(fptr(dz), fptr(w), nullptr, fptr_mut(dx), M, K, N, N, 1, K, 1, K, 0, 0, cur_stream());
+  return dx;
+}
+// dw[N,K] (+)= dz[M,N]^T x[M,K]   (accumulate = add into an existing gradient buffer)
+void linear_f32_wgrad(Tensor dz, Tensor x, Tensor dw, bool accumulate) {
+  CHECK_F32_CUDA(dz); CHECK_F32_CUDA(x); CHECK_F32_CUDA(dw); CHECK_CONTIG(dz); CHECK_CONTIG(x); CHECK_CONTIG(dw);
+  c10::cuda::CUDAGuard guard(dz.device());
+  const int M = (int)dz.size(0), N = (int)dz.size(1), K = (int)x.size(1);
+  TORCH_CHECK(dw.size(0) == N && dw.size(1) == K && x.size(0) == M, "linear_f32_wgrad: shape mismatch");
+  fb::gemm_f32(fptr(dz), fptr(x), nullptr, fptr_mut(dw), N, K, M, 1, N, K, 1, K, 0, accumulate ? 1 : 0, cur_stream());
+}
+// dz = dout * ELU'(z) (act) ; db += column sums of dz.  dz / db optional (pass None).  Tensors are [..., C] contiguous.
+void act_bwd_bias(Tensor dout, c10::optional<Tensor> out, c10::optional<Tensor> dz, c10::optional<Tensor> db, bool act) {
+  CHECK_F32_CUDA(dout); CHECK_CONTIG(dout);
+  c10::cuda::CUDAGuard guard(dout.device());
+  const int C = (int)dout.size(-1);
+  float* dzp = (dz.has_value() && dz->defined()) ? dz->data_ptr<float>() : nullptr;
+  float* dbp = (db.has_value() && db->defined()) ? db->data_ptr<float>() : nullptr;
+  TORCH_CHECK(!act || (out.has_value() && out->defined()), "act_bwd_bias: the activation output is needed for ELU'");
+  fb::act_bwd_bias(fptr(dout), opt_ptr(out), dzp, dbp, (long long)dout.numel(), C, act ? 1 : 0, cur_stream());
+}
+// x: logical NCHW, memory either contiguous NCHW or channels_last (NHWC); the output keeps the input's memory format
+std::vector<Tensor> maxpool2x2_fwd(Tensor x) {
+  CHECK_F32_CUDA(x);
+  TORCH_CHECK(x.dim() == 4, "maxpool2x2: 4-D tensor expected");
+  const bool nhwc = !x.is_contiguous() && x.is_contiguous(at::MemoryFormat::ChannelsLast);
+  TORCH_CHECK(nhwc || x.is_contiguous(), "maxpool2x2: contiguous or channels_last input");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+  auto fmt = nhwc ? at::MemoryFormat::ChannelsLast : at::MemoryFormat::Contiguous;
+  auto y = torch::empty({N, C, H / 2, W / 2}, x.options().memory_format(fmt));
+  auto idx = torch::empty({N, C, H / 2, W / 2}, x.options().dtype(torch::kUInt8).memory_format(fmt));
+  fb::maxpool2x2_fwd(fptr(x), fptr_mut(y), idx.data_ptr<uint8_t>(), N, C, H, W, nhwc ? 1 : 0, cur_stream());
+  return {y, idx};
+}
+Tensor maxpool2x2_bwd(Tensor dy, Tensor idx, int64_t H, int64_t W) {
+  CHECK_F32_CUDA(dy);
+  const bool nhwc = !idx.is_contiguous() && idx.is_contiguous(at::MemoryFormat::ChannelsLast);
+  auto fmt = nhwc ? at::MemoryFormat::ChannelsLast : at::MemoryFormat::Contiguous;
+  Tensor d = dy.contiguous(fmt);
+  c10::cuda::CUDAGuard guard(dy.device());
+  const int N = (int)dy.size(0), C = (int)dy.size(1);
+  auto dx = torch::empty({N, C, H, W}, dy.options().memory_format(fmt));
+  fb::maxpool2x2_bwd(fptr(d), idx.data_ptr<uint8_t>(), fptr_mut(dx), N, C, (int)H, (int)W, nhwc ? 1 : 0, cur_stream());
+  return dx;
+}
+void argmax_count(Tensor logits, Tensor labels, Tensor counter) {
+  CHECK_F32_CUDA(logits); CHECK_CONTIG(logits);
+  TORCH_CHECK(labels.scalar_type() == torch::kInt64 && counter.scalar_type() == torch::kInt64 && counter.numel() >= 2, "argmax_count: int64 labels / counter[2]");
+  c10::cuda::CUDAGuard guard(logits.device());
+  fb::argmax_count(fptr(logits), (const long long*)labels.data_ptr<int64_t>(), (long long*)counter.data_ptr<int64_t>(), (int)logits.size(0),
+                   (int)logits.size(1), cur_stream());
+}
+int64_t info_nce_max_p() { return fb::info_nce_max_p(); }
+int64_t info_nce_scratch_floats() { return fb::info_nce_scratch_floats(); }
+std::vector<Tensor> info_nce_fwd(Tensor Z, Tensor Zh, Tensor scratch) {     // Z, Zh: [R, P]
+  CHECK_F32_CUDA(Z); CHECK_F32_CUDA(Zh); CHECK_CONTIG(Z); CHECK_CONTIG(Zh);
+  c10::cuda::CUDAGuard guard(Z.device());
+  const int R = (int)Z.size(0), P = (int)Z.size(1);
+  auto loss = torch::empty({}, Z.options());
+  auto coef = torch::empty({(int64_t)P * P + 2 * P}, Z.options());
+  fb::info_nce_fwd(fptr(Z), fptr(Zh), R, P, fptr_mut(scratch), fptr_mut(loss), fptr_mut(coef), cur_stream());
+  return {loss, coef};
+}
+std::vector<Tensor> info_nce_bwd(Tensor Z, Tensor Zh, Tensor coef, Tensor gout) {
+  CHECK_F32_CUDA(Z); CHECK_CONTIG(Z); CHECK_CONTIG(Zh);
+  c10::cuda::CUDAGuard guard(Z.device());
+  auto dZ = torch::empty_like(Z), dZh = torch::empty_like(Zh);
+  fb::info_nce_bwd(fptr(Z), fptr(Zh), fptr(coef), fptr(gout), fptr_mut(dZ), fptr_mut(dZh), (int)Z.size(0), (int)Z.size(1), cur_stream());
+  return {dZ, dZh};
+}
+Tensor gauss_nll_rows_fwd(Tensor x, Tensor mu, Tensor s2) {     // x [B, D], mu / s2 [rows, D] with rows % B == 0
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(mu); CHECK_F32_CUDA(s2); CHECK_CONTIG(x); CHECK_CONTIG(mu); CHECK_CONTIG(s2);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int B = (int)x.size(0), D = (int)x.size(1), rows = (int)mu.size(0);
+  TORCH_CHECK(mu.size(1) == D && rows % B == 0, "gauss_nll_rows: mu [k*B, D]");
+  auto out = torch::empty({rows}, x.options());
+  fb::gauss_nll_rows_fwd(fptr(x), fptr(mu), fptr(s2), fptr_mut(out), rows, B, D, cur_stream());
+  return out;
+}
+std::vector<Tensor> gauss_nll_rows_bwd(Tensor x, Tensor mu, Tensor s2, Tensor grow) {
+  CHECK_F32_CUDA(x); CHECK_CONTIG(x); CHECK_CONTIG(mu); CHECK_CONTIG(s2); CHECK_CONTIG(grow);
+  c10::cuda::CUDAGuard guard(x.device());
+  auto dmu = torch::empty_like(mu), ds2 = torch::empty_like(s2);
+  fb::gauss_nll_rows_bwd(fptr(x), fptr(mu), fptr(s2), fptr(grow), fptr_mut(dmu), fptr_mut(ds2), (int)mu.size(0), (int)x.size(0),
+                         (int)x.size(1), cur_stream());
+  return {dmu, ds2};
+}
+// direct small convolutions, NCHW
+bool smallconv_supported(int64_t Ci, int64_t Co, int64_t k) { return fb::smallconv_supported((int)Ci, (int)Co, (int)k); }
+std::vector<Tensor> smallconv_fwd(Tensor x, Tensor w, c10::optional<Tensor> bias, int64_t pad, bool act, bool pool) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), Ci = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3), Co = (int)w.size(0), k = (int)w.size(2);
+  const int Ho = H + 2 * (int)pad - k + 1, Wo = W + 2 * (int)pad - k + 1;
+  auto y = torch::empty({NB, Co, pool ? Ho / 2 : Ho, pool ? Wo / 2 : Wo}, x.options());
+  Tensor idx = pool ? torch::empty(y.sizes(), x.options().dtype(torch::kUInt8)) : torch::empty({0}, x.options().dtype(torch::kUInt8));
+  fb::smallconv_fwd(fptr(x), fptr(w), opt_ptr(bias), fptr_mut(y), pool ? idx.data_ptr<uint8_t>() : nullptr, NB, Ci, H, W, Co, k,
+                    (int)pad, act ? 1 : 0, pool ? 1 : 0, cur_stream());
+  return {y, idx};
+}
+// gradient of the pooled / activated output -> gradient of the pre-activation conv output [NB, Co, Ho, Wo]
+Tensor smallconv_unpool_actbwd(Tensor dy, Tensor yout, Tensor idx, int64_t Ho, int64_t Wo, bool act, bool pool) {
+  CHECK_F32_CUDA(dy); CHECK_CONTIG(dy); CHECK_CONTIG(yout);
+  c10::cuda::CUDAGuard guard(dy.device());
+  auto dz = torch::empty({dy.size(0), dy.size(1), Ho, Wo}, dy.options());
+  fb::smallconv_unpool_actbwd(fptr(dy), fptr(yout), pool ? idx.data_ptr<uint8_t>() : nullptr, fptr_mut(dz),
+                              (long long)(dy.size(0) * dy.size(1)), (int)Ho, (int)Wo, act ? 1 : 0, pool ? 1 : 0, cur_stream());
+  return dz;
+}
+Tensor smallconv_dgrad(Tensor dz, Tensor w, int64_t H, int64_t W, int64_t pad) {
+  CHECK_F32_CUDA(dz); CHECK_CONTIG(dz); CHECK_CONTIG(w);
+  c10::cuda::CUDAGuard guard(dz.device());
+  const int NB = (int)dz.size(0), Co = (int)w.size(0), Ci = (int)w.size(1), k = (int)w.size(2);
+  auto dx = torch::empty({NB, Ci, H, W}, dz.options());
+  fb::smallconv_dgrad(fptr(dz), fptr(w), fptr_mut(dx), NB, Ci, (int)H, (int)W, Co, k, (int)pad, cur_stream());
+  return dx;
+}
+void smallconv_wgrad(Tensor dz, Tensor x, Tensor dw, c10::optional<Tensor> db, int64_t pad) {   // dw / db are accumulated into
+  CHECK_F32_CUDA(dz); CHECK_CONTIG(dz); CHECK_CONTIG(x); CHECK_CONTIG(dw);
+  c10::cuda::CUDAGuard guard(dz.device());
+  const int NB = (int)x.size(0), Ci = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3), Co = (int)dw.size(0), k = (int)dw.size(2);
+  float* dbp = (db.has_value() && db->defined()) ? db->data_ptr<float>() : nullptr;
+  fb::smallconv_wgrad(fptr(dz), fptr(x), fptr_mut(dw), dbp, NB, Ci, H, W, Co, k, (int)pad, cur_stream());
 }
 
 // ---------------------------------------------------------------------------------------------- collectives
@@ -446,10 +606,30 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv2d_nhwc_sized", &conv2d_nhwc_sized);
   m.def("conv2d_nhwc_bias_act", &conv2d_nhwc_bias_act);
   m.def("conv2d_nhwc_accumulate", &conv2d_nhwc_accumulate);
+  m.def("conv_wgrad", &conv_wgrad);
+  m.def("conv_wgrad_supported", &conv_wgrad_supported);
   m.def("cross_entropy_fwd", &cross_entropy_fwd);
   m.def("cross_entropy_bwd", &cross_entropy_bwd);
   m.def("vae_loss_fwd", &vae_loss_fwd);
   m.def("vae_loss_bwd", &vae_loss_bwd);
+  m.def("linear_f32", &linear_f32);
+  m.def("linear_f32_dgrad", &linear_f32_dgrad);
+  m.def("linear_f32_wgrad", &linear_f32_wgrad);
+  m.def("act_bwd_bias", &act_bwd_bias);
+  m.def("maxpool2x2_fwd", &maxpool2x2_fwd);
+  m.def("maxpool2x2_bwd", &maxpool2x2_bwd);
+  m.def("argmax_count", &argmax_count);
+  m.def("info_nce_max_p", &info_nce_max_p);
+  m.def("info_nce_scratch_floats", &info_nce_scratch_floats);
+  m.def("info_nce_fwd", &info_nce_fwd);
+  m.def("info_nce_bwd", &info_nce_bwd);
+  m.def("gauss_nll_rows_fwd", &gauss_nll_rows_fwd);
+  m.def("gauss_nll_rows_bwd", &gauss_nll_rows_bwd);
+  m.def("smallconv_supported", &smallconv_supported);
+  m.def("smallconv_fwd", &smallconv_fwd);
+  m.def("smallconv_unpool_actbwd", &smallconv_unpool_actbwd);
+  m.def("smallconv_dgrad", &smallconv_dgrad);
+  m.def("smallconv_wgrad", &smallconv_wgrad);
   m.def("block_reduce", &block_reduce);
   m.def("bb_update", &bb_update);
   m.def("ipc_get_handle", &ipc_get_handle);

@@ -55,6 +55,11 @@ void conv2d_nhwc_bias_act_tf32(const float* x, const float* w, const float* bias
                                int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
                                cudaStream_t stream);
 
+// weight gradient on tcgen05 (MN-major operands, split over the pixel range, red.add into dw)
+bool conv_wgrad_supported(int C_x, int C_out, int stride, int W_out, int H_out);
+void conv_wgrad_tf32(const float* x, const float* dy, float* dw, int NB, int H, int W, int C_x, int C_w, int C_out, int kh,
+                     int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream);
+
 void set_conv_trace(long long* buf);   // [16] clock64 stamps of CTA 0 of the next persistent conv launches (nullptr = off)
 void probe_launch(int kind, int grid, int smem_bytes, cudaStream_t stream);   // launch-floor probes (tools/)
 
@@ -111,6 +116,30 @@ void vae_loss_fwd(const float* recon, const float* x, int n, const float* mu, co
                   cudaStream_t s);
 void vae_loss_bwd(const float* recon, const float* x, int n, const float* mu, const float* logvar, int nl,
                   const float* gout, float* drecon, float* dmu, float* dlogvar, cudaStream_t s);
+
+// ---- small / awkward operators in true fp32 (aux_kernels.cu) ---------------------------------------
+void gemm_f32(const float* a, const float* b, const float* bias, float* c, int M, int N, int K, long long sa_i, long long sa_k,
+              long long sb_k, long long sb_j, int ldc, int act, int accumulate, cudaStream_t s);
+void act_bwd_bias(const float* dout, const float* out, float* dz, float* db, long long total, int C, int act, cudaStream_t s);
+void maxpool2x2_fwd(const float* x, float* y, unsigned char* idx, int N, int C, int H, int W, int nhwc, cudaStream_t s);
+void maxpool2x2_bwd(const float* dy, const unsigned char* idx, float* dx, int N, int C, int H, int W, int nhwc, cudaStream_t s);
+void argmax_count(const float* logits, const long long* labels, long long* counter, int B, int C, cudaStream_t s);
+int info_nce_max_p();
+int info_nce_scratch_floats();
+void info_nce_fwd(const float* Z, const float* Zh, int R, int P, float* scratch, float* loss, float* coef, cudaStream_t s);
+void info_nce_bwd(const float* Z, const float* Zh, const float* coef, const float* gout, float* dZ, float* dZh, int R, int P,
+                  cudaStream_t s);
+void gauss_nll_rows_fwd(const float* x, const float* mu, const float* s2, float* rows, int nrows, int B, int D, cudaStream_t s);
+void gauss_nll_rows_bwd(const float* x, const float* mu, const float* s2, const float* grow, float* dmu, float* ds2, int nrows,
+                        int B, int D, cudaStream_t s);
+bool smallconv_supported(int Ci, int Co, int k);
+void smallconv_fwd(const float* x, const float* w, const float* bias, float* y, unsigned char* pidx, int NB, int Ci, int H, int W,
+                   int Co, int k, int pad, int act, int pool, cudaStream_t s);
+void smallconv_dgrad(const float* dz, const float* w, float* dx, int NB, int Ci, int H, int W, int Co, int k, int pad, cudaStream_t s);
+void smallconv_wgrad(const float* dz, const float* x, float* dw, float* db, int NB, int Ci, int H, int W, int Co, int k, int pad,
+                     cudaStream_t s);
+void smallconv_unpool_actbwd(const float* dy, const float* yout, const unsigned char* pidx, float* dz, long long planes, int Ho, int Wo,
+                             int act, int pool, cudaStream_t s);
 
 // ---- fused block collectives (comm_kernels.cu) -------------------------------------------------------
 constexpr int COMM_MAX_K = 64;       // contributions (workers) per aggregation

@@ -6,7 +6,9 @@
 #include "conv_halo_tcgen05.cuh"
 #include "igemm2_tcgen05.cuh"
 #include "conv_ws_tcgen05.cuh"
+#include "wgrad_tcgen05.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <stdexcept>
@@ -537,6 +539,107 @@ static void conv2d_generic(const float* x, const float* w, float* y, float* stat
   }
   if (pair) dispatch2(bn, ta, tb, p, stream); else dispatch(bn, cl, ta, tb, p, stream);
   if (p.k_splits > 1 && stats != nullptr) col_stats(y, stats, M, C_out, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient (wgrad_tcgen05.cuh)
+// ------------------------------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// NHWC tensor viewed as [C, W, H, N]; box = 32 channels x (bw x bh x bn) pixels visited with traversal stride `st`
+static CUtensorMap make_tmap_pixels(const float* ptr, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t bn, uint32_t bh,
+                                    uint32_t bw, uint32_t st) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
+  cuuint32_t box[4] = {32, bw * st, bh * st, bn};
+  cuuint32_t estr[4] = {1, st, st, 1};
+  // 128-byte swizzle with a 32-byte atom: the only layout the tensor core reads MN-major tf32 operands from
+  check_cu(encode_fn()(&m, tmap_dtype(), 4, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+           "cuTensorMapEncodeTiled(pixels)");
+  return m;
+}
+
+bool conv_wgrad_supported(int C_x, int C_out, int stride, int W_out, int H_out) {
+  if ((C_x & 3) || (C_out & 3)) return false;             // 16-byte pixel pitch for TMA
+  if (stride < 1 || stride > 8) return false;
+  const int WB = std::min(32, pow2_ceil(W_out));
+  const int HB = std::min(32 / WB, pow2_ceil(H_out));
+  return WB * stride <= 256 && HB * stride <= 256;
+}
+
+// dw [C_out, kh, kw, C_w] += wgrad(x [NB,H,W,C_x], dy [NB,H_out,W_out,C_out]); only the first C_w input channels are
+// produced (C_w < C_x when the activation was channel-padded for TMA, e.g. the 3 -> 4 channel stem input).
+void conv_wgrad_tf32(const float* x, const float* dy, float* dw, int NB, int H, int W, int C_x, int C_w, int C_out, int kh,
+                     int kw, int stride, int pad, int dil, int H_out, int W_out, cudaStream_t stream) {
+  if (!conv_wgrad_supported(C_x, C_out, stride, W_out, H_out))
+    throw std::runtime_error("fedb200: wgrad geometry not supported by the tcgen05 path");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dy) & 15))
+    throw std::runtime_error("fedb200: wgrad needs 16-byte aligned activations");
+  WgradParams p{};
+  p.kw = kw; p.taps = kh * kw; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.Co = C_out; p.Cw = C_w;
+  p.nbox_ci = (C_w + 31) / 32;
+  p.nbox_a = p.taps * p.nbox_ci;
+  p.g_total = (p.nbox_a + 3) / 4;
+  p.WB = std::min(32, pow2_ceil(W_out));
+  p.HB = std::min(WG_BK / p.WB, pow2_ceil(H_out));
+  p.NBX = WG_BK / (p.WB * p.HB);
+  p.blocks_w = (W_out + p.WB - 1) / p.WB;
+  p.blocks_h = (H_out + p.HB - 1) / p.HB;
+  const int blocks_n = (NB + p.NBX - 1) / p.NBX;
+  p.kb_total = blocks_n * p.blocks_h * p.blocks_w;
+  // N tile: all output channels when they fit in 128 columns
+  p.nb = C_out <= 32 ? 1 : (C_out <= 64 ? 2 : 4);
+  const int co_t = p.nb * 32;
+  p.co_tiles = (C_out + co_t - 1) / co_t;
+  // groups per CTA: TMEM (512 columns) and shared memory (a stage = (4 gpc + nb) boxes of 4 KB, >= 2 stages in ~200 KB)
+  int gpc = std::min(p.g_total, 512 / co_t);
+  gpc = std::min(gpc, env_int("FEDB200_WGRAD_GPC", 4));
+  while ((4 * gpc + p.nb) * WG_BOX_BYTES * 2 > 200 * 1024 && gpc > 1) --gpc;
+  p.gpc = gpc;
+  p.g_units = (p.g_total + gpc - 1) / gpc;
+  p.stage_bytes = (4 * gpc + p.nb) * WG_BOX_BYTES;
+  p.stages = std::min(WG_MAX_STAGES, (200 * 1024) / p.stage_bytes);
+  if (p.stages < 2) throw std::runtime_error("fedb200: wgrad stage does not fit twice in shared memory");
+  uint32_t cols = 32;
+  while (cols < uint32_t(gpc * co_t)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.dw = dw;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  // split the pixel range until ~two waves of CTAs exist, but keep >= 4 k-blocks per CTA (prologue + red.add epilogue)
+  const int base = p.g_units * p.co_tiles;
+  int splits = env_int("FEDB200_WGRAD_SPLITS", 0);
+  if (splits <= 0) {
+    splits = std::max(1, (2 * sms) / base);
+    splits = std::min(splits, std::max(1, p.kb_total / 4));
+  }
+  splits = std::min(splits, p.kb_total);
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;       // no empty slices
+  const CUtensorMap tx = make_tmap_pixels(x, NB, H, W, C_x, p.NBX, p.HB, p.WB, stride);
+  const CUtensorMap tdy = make_tmap_pixels(dy, NB, H_out, W_out, C_out, p.NBX, p.HB, p.WB, 1);
+  const int smem = p.stages * p.stage_bytes + (2 * WG_MAX_STAGES + 2) * 8 + 16 + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(wgrad): ") + cudaGetErrorString(e));
+    configured = 227 * 1024;
+  }
+  cudaError_t e = launch_pdl(wgrad_tf32_kernel, dim3(base * splits), dim3(WG_THREADS), size_t(smem), stream, tx, tdy, p);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: wgrad launch: ") + cudaGetErrorString(e));
+  count_launch();
 }
 
 // ---- launch-floor probes (tools/probe_launch.py): how long does a kernel that does nothing take inside a graph? ----

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .base import BlockPartitioned
+from ..ops import functional as FX
 
 
 class _PlanNet(BlockPartitioned):
@@ -42,9 +43,7 @@ class _PlanNet(BlockPartitioned):
 
     def features(self, x: torch.Tensor) -> torch.Tensor:
         for attr, _cin, _cout, _k, _pad, pool in self.CONV_PLAN:
-            x = F.elu(getattr(self, attr)(x))
-            if pool:
-                x = F.max_pool2d(x, 2, 2)
+            x = FX.conv_act_pool(x, getattr(self, attr), act=True, pool=bool(pool))     # conv + bias + ELU (+ pool) fused
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -52,9 +51,7 @@ class _PlanNet(BlockPartitioned):
         x = x.reshape(x.shape[0], -1)
         last = len(self.FC_PLAN) - 1
         for i, (attr, _fin, _fout) in enumerate(self.FC_PLAN):
-            x = getattr(self, attr)(x)
-            if i != last:
-                x = F.elu(x)
+            x = FX.linear_act(x, getattr(self, attr), act=(i != last))                 # GEMM + bias + ELU epilogue
         return x
 
 

@@ -38,7 +38,7 @@ class EncoderCNN(BlockPartitioned):
         h = torch.cat(stem, dim=1)
         for name in ("conv2", "conv3", "conv4"):
             h = FX.conv_act(h, getattr(self, name))
-        return F.avg_pool2d(h, 2).squeeze()
+        return FX.global_avg_pool(h) if (h.shape[2] == 2 and h.shape[3] == 2 and h.shape[0] > 1) else F.avg_pool2d(h, 2).squeeze()
 
 
 class ContextgenCNN(BlockPartitioned):
@@ -71,4 +71,4 @@ class PredictorCNN(BlockPartitioned):
         self.conv2 = nn.Conv2d(latent_dim, reduced_dim, 1, bias=False)
 
     def forward(self, latents: torch.Tensor, context: torch.Tensor):
-        return self.conv1(latents), self.conv2(context)
+        return FX.conv_act(latents, self.conv1, act=False), FX.conv_act(context, self.conv2, act=False)

@@ -68,14 +68,14 @@ class AutoEncoderCNN(_ConvEncoderMixin, BlockPartitioned):
 
     def encode(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         h = FX.linear_act(self.conv_features(x), self.fc1)
-        return self.fc21(h), self.fc22(h)
+        return FX.linear_act(h, self.fc21, act=False), FX.linear_act(h, self.fc22, act=False)
 
     def reparametrize(self, mu: torch.Tensor, logvar: torch.Tensor) -> torch.Tensor:
         std = torch.exp(0.5 * logvar)
         return mu + torch.randn_like(std) * std
 
     def decode(self, z: torch.Tensor) -> torch.Tensor:
-        h = self.fc3(z).reshape(-1, 96, 2, 2)
+        h = FX.linear_act(z, self.fc3, act=False).reshape(-1, 96, 2, 2)
         for i in range(1, 5):
             h = FX.conv_act(h, getattr(self, "tconv%d" % i))
         return torch.sigmoid(h)
@@ -150,7 +150,7 @@ class AutoEncoderCNNCL(_ConvEncoderMixin, BlockPartitioned):
 
     def decode(self, ek: torch.Tensor, z: torch.Tensor):
         h = FX.linear_act(FX.linear_act(ek, self.fc14), self.fc15)
-        mu_b, sig2_b = self.fc16(h), F.softplus(self.fc17(h))
+        mu_b, sig2_b = FX.linear_act(h, self.fc16, act=False), F.softplus(FX.linear_act(h, self.fc17, act=False))
         g = FX.linear_act(z, self.fc25).reshape(-1, 96, 2, 2)
         for name in ("tconv1", "tconv2", "tconv3"):
             g = FX.conv_act(g, getattr(self, name))

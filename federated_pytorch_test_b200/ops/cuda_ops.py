@@ -272,6 +272,62 @@ def _s2_dgrad(e, dy: torch.Tensor, wk: torch.Tensor, trainable: bool, persistent
     return conv_math.dgrad_s2(dy, wp, lambda x, w: e.conv2d_nhwc_sized(x, w, None, 1, 0, 1, Ho, Wo))
 
 
+# ----------------------------------------------------------------------------
+# weight gradient on tcgen05 (csrc/wgrad_tcgen05.cuh): MN-major operands straight from the NHWC activations,
+# split over the pixel range, partial sums red.add-ed into dW
+# ----------------------------------------------------------------------------
+WGRAD = os.environ.get("FEDB200_WGRAD", "1") != "0"
+_ACC_INTO_GRAD = {"on": False}
+
+
+class accumulate_into_grad:
+    """Context manager for ``loss.backward()`` calls of the engine: while active, weight-gradient kernels accumulate
+    straight into the parameter's ``.grad`` buffer (a zeroed view of the gradient arena) and the autograd node returns
+    ``None`` for the weight, which removes one fill and one ``add`` launch per trainable convolution / dense layer.
+    Never active under ``torch.autograd.grad`` (functional calls must not touch ``.grad``)."""
+
+    def __enter__(self):
+        self.prev = _ACC_INTO_GRAD["on"]
+        _ACC_INTO_GRAD["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        _ACC_INTO_GRAD["on"] = self.prev
+        return False
+
+
+def _grad_buffer_krsc(weight: Optional[torch.Tensor], shape_krsc) -> Optional[torch.Tensor]:
+    """The parameter's gradient buffer as a contiguous [Co, kh, kw, Ci] tensor, if in-place accumulation is allowed."""
+    if not _ACC_INTO_GRAD["on"] or weight is None or getattr(weight, "grad", None) is None:
+        return None
+    g = weight.grad
+    if g.dim() != 4:
+        return None
+    gk = g.permute(0, 2, 3, 1)
+    if not gk.is_contiguous() or tuple(gk.shape) != tuple(shape_krsc) or g.dtype != torch.float32:
+        return None
+    return gk
+
+
+def conv_wgrad_supported(xn: torch.Tensor, dy: torch.Tensor, stride: int) -> bool:
+    return bool(WGRAD and ext().conv_wgrad_supported(xn.shape[3], dy.shape[3], stride, dy.shape[2], dy.shape[1]))
+
+
+def conv_wgrad(xn: torch.Tensor, dy: torch.Tensor, kh: int, kw: int, cw: int, stride: int, pad: int, dil: int,
+               weight: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """dW of ``conv(x, W)`` from NHWC ``xn`` [N,H,W,Cx] and ``dy`` [N,Ho,Wo,Co]: returns the gradient as a logical
+    [Co, cw, kh, kw] tensor (KRSC memory), or ``None`` after accumulating into ``weight.grad`` in place."""
+    Co = dy.shape[3]
+    dyc = dy if dy.is_contiguous() else dy.contiguous()
+    buf = _grad_buffer_krsc(weight, (Co, kh, kw, cw))
+    if buf is not None:
+        ext().conv_wgrad(xn, dyc, buf, stride, pad, dil)
+        return None
+    dwk = torch.zeros(Co, kh, kw, cw, dtype=torch.float32, device=xn.device)
+    ext().conv_wgrad(xn, dyc, dwk, stride, pad, dil)
+    return dwk.permute(0, 3, 1, 2)
+
+
 class _ConvBnAct(torch.autograd.Function):
     """``act(BN_train(conv(x)) + residual)`` with NHWC kernels; see module docstring."""
 
@@ -291,6 +347,7 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.save_for_backward(xn, wk, y, out, mean, invstd, gamma, beta)
         ctx.cfg = (stride, pad, act, residual is not None, tuple(weight.shape), x.shape[1])
         ctx.w_persistent = _aliases(wk, weight)
+        ctx.weight_ref = weight
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -323,10 +380,13 @@ class _ConvBnAct(torch.autograd.Function):
                 dxn = dxn[..., :cin_logical]
             dx = dxn.permute(0, 3, 1, 2)
         if need_w:
-            dwk = torch.ops.aten.convolution_backward(
-                dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
-                [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
-            dw = dwk[:, :cin_logical] if dwk.shape[1] != cin_logical else dwk
+            if conv_wgrad_supported(xn, dy, stride):
+                dw = conv_wgrad(xn, dy, kh, kw, cin_logical, stride, pad, 1, ctx.weight_ref)
+            else:
+                dwk = torch.ops.aten.convolution_backward(
+                    dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
+                    [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+                dw = dwk[:, :cin_logical] if dwk.shape[1] != cin_logical else dwk
         dr = dres.permute(0, 3, 1, 2) if (has_res and need_r and dres is not None) else None
         return dx, dw, dgamma, dbeta, dr, None, None, None, None, None, None, None
 
@@ -356,6 +416,7 @@ class _ConvBnActSkip(torch.autograd.Function):
         ctx.save_for_backward(xn, wk, y, mean, invstd, gamma, beta)
         ctx.cfg = (stride, pad, tuple(weight.shape))
         ctx.w_persistent = _aliases(wk, weight)
+        ctx.weight_ref = weight
         return out.permute(0, 3, 1, 2), x.view_as(x)
 
     @staticmethod
@@ -382,9 +443,12 @@ class _ConvBnActSkip(torch.autograd.Function):
         elif dskip is not None:
             dx = dskip
         if need_w:
-            dw = torch.ops.aten.convolution_backward(
-                dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
-                [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
+            if conv_wgrad_supported(xn, dy, stride):
+                dw = conv_wgrad(xn, dy, kh, wshape[3], wshape[1], stride, pad, 1, ctx.weight_ref)
+            else:
+                dw = torch.ops.aten.convolution_backward(
+                    dy.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), wk.permute(0, 3, 1, 2), None,
+                    [stride, stride], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False])[1]
         return dx, dw, dgamma, dbeta, None, None, None, None, None, None
 
 
@@ -401,11 +465,16 @@ def conv_bn_act_skip(x, conv: nn.Conv2d, bn: nn.BatchNorm2d):
 
 
 # ----------------------------------------------------------------------------
-# conv + bias (+ ELU) of the VAE / CPC networks: forward on the implicit-GEMM kernel, backward on ATen.
-# Opt-in in this round (FEDB200_CONV_ACT=1): the kernel-level checks of tests/test_gpu_experimental.py pass on a B200
-# (profiles/r1_run22_*), the VAE / CPC drivers have not been run with it yet.
+# conv + bias (+ ELU) of the VAE / CPC networks — forward AND backward on hand-written kernels:
+#   forward   implicit GEMM on tcgen05 with bias + ELU in the epilogue (transposed convs: 3x3 conv with 4*C_out phase
+#             channels + pixel shuffle, ops/conv_math.py)
+#   dz, db    one pass: dout * ELU'(z) recomputed from the saved output + per-channel sums   (act_bwd_bias kernel)
+#   dx        stride-2 4x4: the transposed-conv kernel path with the same weights; stride 1: rotated filter;
+#             transposed conv: the forward stride-2 conv kernel
+#   dw        tcgen05 weight-gradient kernel (wgrad_tcgen05.cuh); for transposed convs with the roles of x and dz swapped
+# FEDB200_CONV_ACT=0 restores the ATen / cuDNN composition (A/B runs).
 # ----------------------------------------------------------------------------
-CONV_ACT = os.environ.get("FEDB200_CONV_ACT", "0") == "1"
+CONV_ACT = os.environ.get("FEDB200_CONV_ACT", "1") != "0"
 
 
 def conv_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
@@ -426,36 +495,80 @@ def conv_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
     return bool(ext().conv_supported(Ho, Wo, Ci if Ci != 3 else 4, s))
 
 
+def _act_bwd_bias(d: torch.Tensor, out: torch.Tensor, act: bool, need_b: bool, bias_param=None):
+    """(dz, db): dz = d * ELU'(z) (aliasing ``d`` when there is no activation); db = per-channel sums (or None after
+    accumulating into ``bias_param.grad`` inside ``accumulate_into_grad``)."""
+    e = ext()
+    d = d if d.is_contiguous() else d.contiguous()
+    C = d.shape[-1]
+    db = None
+    dbuf = None
+    if need_b:
+        if _ACC_INTO_GRAD["on"] and bias_param is not None and getattr(bias_param, "grad", None) is not None \
+                and bias_param.grad.is_contiguous() and bias_param.grad.numel() == C:
+            dbuf = bias_param.grad
+        else:
+            db = torch.zeros(C, dtype=torch.float32, device=d.device)
+            dbuf = db
+    if not act and dbuf is None:
+        return d, None
+    dz = torch.empty_like(d) if act else None
+    e.act_bwd_bias(d, out if act else None, dz, dbuf, bool(act))
+    return (dz if act else d), db
+
+
 class _ConvAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad, dil, act):
         xn = _nhwc(x)
         wk = _krsc(weight)
+        ci_logical = xn.shape[3]
         if xn.shape[3] == 3:   # 16-byte pixel pitch for the TMA box
             xn = F.pad(xn, (0, 1))
             wk = F.pad(wk, (0, 1))
         out = ext().conv2d_nhwc_bias_act(xn, wk, bias, bool(act), stride, pad, dil)
-        ctx.save_for_backward(x, weight, out)
-        ctx.cfg = (stride, pad, dil, act, bias is not None)
+        ctx.save_for_backward(xn, weight, out)
+        ctx.cfg = (stride, pad, dil, act, bias is not None, ci_logical)
+        ctx.params = (weight, bias)
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, out = ctx.saved_tensors
-        stride, pad, dil, act, has_bias = ctx.cfg
-        d = _nhwc(dout)
-        if act:   # ELU'(z) from the output: z > 0 <=> out > 0, exp(z) = out + 1
-            d = d * torch.where(out > 0, torch.ones_like(out), out + 1.0)
+        e = ext()
+        xn, weight, out = ctx.saved_tensors
+        stride, pad, dil, act, has_bias, ci_logical = ctx.cfg
+        wparam, bparam = ctx.params
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and has_bias
-        dx, dw, db = torch.ops.aten.convolution_backward(
-            d.permute(0, 3, 1, 2), x, weight, [weight.shape[0]] if has_bias else None, [stride, stride], [pad, pad], [dil, dil],
-            False, [0, 0], 1, [bool(need_x), bool(need_w), bool(need_b)])
-        return (dx if need_x else None), (dw if need_w else None), (db if need_b else None), None, None, None, None
+        dz, db = _act_bwd_bias(_nhwc(dout), out, act, need_b, bparam)
+        Co, _, k, _ = weight.shape
+        Ho, Wo = dz.shape[1], dz.shape[2]
+        dx = dw = None
+        if need_x:
+            dxn = None
+            if stride == 2 and k == 4 and pad == 1 and dil == 1 and Co % 4 == 0 and e.conv_supported(Ho, Wo, Co, 1):
+                # data gradient of conv(4, s2, p1) == ConvTranspose2d(4, s2, p1) with the same weight tensor
+                wp = conv_math.pack_convT_s2_weight(weight)
+                dxn = conv_math.convT_s2(dz, wp, lambda a, w: e.conv2d_nhwc_bias_act(a, w, None, False, 1, 1, 1))
+            elif stride == 1 and dil == 1 and Co % 4 == 0 and e.conv_supported(xn.shape[1], xn.shape[2], Co, 1):
+                dxn = e.conv2d_nhwc(dz, e.weight_flip(_krsc(weight).contiguous()), None, 1, k - 1 - pad, 1)
+            if dxn is None:
+                dxn = _nhwc(torch.ops.aten.convolution_backward(
+                    dz.permute(0, 3, 1, 2), xn[..., :ci_logical].permute(0, 3, 1, 2), weight, None, [stride, stride], [pad, pad],
+                    [dil, dil], False, [0, 0], 1, [True, False, False])[0])
+            dx = dxn[..., :ci_logical].permute(0, 3, 1, 2) if dxn.shape[3] != ci_logical else dxn.permute(0, 3, 1, 2)
+        if need_w:
+            if conv_wgrad_supported(xn, dz, stride):
+                dw = conv_wgrad(xn, dz, k, k, ci_logical, stride, pad, dil, wparam)
+            else:
+                dw = torch.ops.aten.convolution_backward(
+                    dz.permute(0, 3, 1, 2), xn[..., :ci_logical].permute(0, 3, 1, 2), weight, None, [stride, stride], [pad, pad],
+                    [dil, dil], False, [0, 0], 1, [False, True, False])[1]
+        return dx, dw, (db if need_b else None), None, None, None, None
 
 
 def conv_transpose_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
     """ConvTranspose2d(k=4, stride=2, padding=1) of the VAE decoders as one 3x3 convolution with 4*C_out
-    phase channels + pixel shuffle (conv_math.pack_convT_s2_weight).  Same opt-in switch as conv_act."""
+    phase channels + pixel shuffle (conv_math.pack_convT_s2_weight)."""
     if not CONV_ACT or not isinstance(conv, nn.ConvTranspose2d) or x.dim() != 4 or x.dtype != torch.float32:
         return False
     if (tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding), tuple(conv.output_padding), tuple(conv.dilation),
@@ -473,22 +586,55 @@ class _ConvTransposeAct(torch.autograd.Function):
         b4 = bias.repeat(4) if bias is not None else None          # phase-major channels (ph, pw, co)
         e = ext()
         out = conv_math.convT_s2(xn, wp, lambda a, w: e.conv2d_nhwc_bias_act(a, w, b4, bool(act), 1, 1, 1))
-        ctx.save_for_backward(x, weight, out)
+        ctx.save_for_backward(xn, weight, out)
         ctx.cfg = (act, bias is not None)
+        ctx.params = (weight, bias)
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, out = ctx.saved_tensors
+        e = ext()
+        xn, weight, out = ctx.saved_tensors
         act, has_bias = ctx.cfg
-        d = _nhwc(dout)
-        if act:
-            d = d * torch.where(out > 0, torch.ones_like(out), out + 1.0)
+        _, bparam = ctx.params
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and has_bias
-        dx, dw, db = torch.ops.aten.convolution_backward(
-            d.permute(0, 3, 1, 2), x, weight, [weight.shape[1]] if has_bias else None, [2, 2], [1, 1], [1, 1], True, [0, 0], 1,
-            [bool(need_x), bool(need_w), bool(need_b)])
-        return (dx if need_x else None), (dw if need_w else None), (db if need_b else None), None
+        dz, db = _act_bwd_bias(_nhwc(dout), out, act, need_b, bparam)      # [N, 2H, 2W, Co]
+        Ci, Co = weight.shape[0], weight.shape[1]
+        H, W = xn.shape[1], xn.shape[2]
+        dzp = dz if Co % 4 == 0 else F.pad(dz, (0, 4 - Co % 4))           # 16-byte pixel pitch for TMA
+        dx = dw = None
+        if need_x:
+            # dx = conv(dz, W) with stride 2, pad 1 where W is read as a conv filter [out = Ci, in = Co, 4, 4]
+            wk = weight.permute(0, 2, 3, 1)
+            wk = wk if Co % 4 == 0 else F.pad(wk, (0, 4 - Co % 4))
+            if e.conv_supported(H, W, dzp.shape[3], 2):
+                dx = e.conv2d_nhwc(dzp, wk.contiguous(), None, 2, 1, 1).permute(0, 3, 1, 2)
+            else:
+                dx = torch.ops.aten.convolution_backward(dz.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), weight, None, [2, 2], [1, 1],
+                                                         [1, 1], True, [0, 0], 1, [True, False, False])[0]
+        if need_w:
+            if conv_wgrad_supported(dzp, xn, 2):
+                # weight gradient with the roles swapped: "input" = dz (large map), "output gradient" = x (small map)
+                dw = conv_wgrad(dzp, xn, 4, 4, Co, 2, 1, 1, None)          # logical [Ci, Co, 4, 4] == the transposed-conv weight
+            else:
+                dw = torch.ops.aten.convolution_backward(dz.permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), weight, None, [2, 2], [1, 1],
+                                                         [1, 1], True, [0, 0], 1, [False, True, False])[1]
+        return dx, dw, (db if need_b else None), None
+
+
+def conv1x1_supported(x: torch.Tensor, conv: nn.Module) -> bool:
+    """1x1 / stride 1 / no padding convolutions on maps the TMA path cannot tile (the 3x3 CPC latent grid)
+    are plain GEMMs over the [N*H*W, C] pixel rows: they run on the dense-layer kernels."""
+    return (CONV_ACT and isinstance(conv, nn.Conv2d) and not isinstance(conv, nn.ConvTranspose2d) and x.dim() == 4
+            and x.dtype == torch.float32 and tuple(conv.kernel_size) == (1, 1) and tuple(conv.stride) == (1, 1)
+            and not isinstance(conv.padding, str) and tuple(conv.padding) == (0, 0) and conv.groups == 1)
+
+
+def conv1x1_linear(x: torch.Tensor, conv: nn.Conv2d, act: bool) -> torch.Tensor:
+    N, C, H, W = x.shape
+    rows = x.permute(0, 2, 3, 1).reshape(N * H * W, C)
+    out = _LinearAct.apply(rows, conv.weight.view(conv.out_channels, C), conv.bias, bool(act))
+    return out.view(N, H, W, conv.out_channels).permute(0, 3, 1, 2)
 
 
 def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor:
@@ -522,11 +668,25 @@ class _AvgPoolNHWC(torch.autograd.Function):
         return dx.permute(0, 3, 1, 2)
 
 
-HEAD_FUSED = os.environ.get("FEDB200_HEAD_FUSED", "0") == "1"   # experimental, see tests/test_gpu_experimental.py
+HEAD_FUSED = os.environ.get("FEDB200_HEAD_FUSED", "1") != "0"   # confirmed on a B200 (profiles/r2_*): default on
+
+
+def _dense_wgrad(dz: torch.Tensor, x: torch.Tensor, wparam) -> Optional[torch.Tensor]:
+    """dW [N, K] = dz^T x in true fp32: accumulated into ``wparam.grad`` when allowed (returns None), else returned."""
+    e = ext()
+    N, K = dz.shape[1], x.shape[1]
+    if _ACC_INTO_GRAD["on"] and wparam is not None and getattr(wparam, "grad", None) is not None \
+            and wparam.grad.is_contiguous() and tuple(wparam.grad.shape) == (N, K):
+        e.linear_f32_wgrad(dz, x, wparam.grad, True)
+        return None
+    dw = torch.empty(N, K, dtype=torch.float32, device=dz.device)
+    e.linear_f32_wgrad(dz, x, dw, False)
+    return dw
 
 
 class _PoolLinear(torch.autograd.Function):
-    """avg_pool over the whole map + Linear in one true-fp32 kernel per direction (experimental, opt-in)."""
+    """avg_pool over the whole map + Linear in one true-fp32 kernel per direction; weight / bias gradients on the fp32
+    GEMM and column-sum kernels (no cuBLAS call left in the classifier head)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -535,15 +695,19 @@ class _PoolLinear(torch.autograd.Function):
         ctx.save_for_backward(weight, pooled)
         ctx.hw = (xn.shape[1], xn.shape[2])
         ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         weight, pooled = ctx.saved_tensors
+        wparam, bparam = ctx.params
         dl = dlogits.contiguous()
         dx = ext().head_bwd(dl, weight.contiguous(), ctx.hw[0], ctx.hw[1]).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None
-        dw = dl.t() @ pooled if ctx.needs_input_grad[1] else None          # only when the classifier block is the active one
-        db = dl.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dw = _dense_wgrad(dl, pooled, wparam) if ctx.needs_input_grad[1] else None     # only when the classifier block is active
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            _, db = _act_bwd_bias(dl, None, False, True, bparam)
         return dx, dw, db
 
 
@@ -551,33 +715,46 @@ def pool_linear(x, linear: nn.Linear, window: int) -> torch.Tensor:
     if HEAD_FUSED and linear.out_features <= 32:
         return _PoolLinear.apply(x, linear.weight, linear.bias)
     pooled = _AvgPoolNHWC.apply(x)                     # global average over the window x window map
-    return F.linear(pooled, linear.weight, linear.bias)  # 128x512x10: true fp32, as in the reference
+    return linear_act(pooled, linear, False)
 
 
 # ----------------------------------------------------------------------------
-# dense layers on tensor cores (opt-in: the reference runs nn.Linear in true fp32)
+# dense layers.  Default: hand-written TRUE-fp32 kernels (the reference's nn.Linear precision, any shape:
+# 128x10x512 classifier, 400->120->84->10 of Net, the VAE / VAE-CL heads) with bias + ELU in the GEMM epilogue;
+# FEDB200_TF32_LINEAR=1 routes 16-byte aligned layers to the tcgen05 GEMM (TF32 products) instead.
 # ----------------------------------------------------------------------------
+LINEAR_F32 = os.environ.get("FEDB200_LINEAR_F32", "1") != "0"
+
+
 def linear_act_supported(x, linear) -> bool:
-    return (TF32_LINEAR and x.dim() == 2 and x.dtype == torch.float32 and x.shape[1] % 4 == 0
-            and x.is_contiguous() and linear.weight.is_contiguous())
+    if not (x.dim() == 2 and x.dtype == torch.float32 and isinstance(linear, nn.Linear)):
+        return False
+    return LINEAR_F32 or TF32_LINEAR
 
 
 class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, act):
-        out = ext().linear_tf32(x, w, b, act)
-        ctx.save_for_backward(x, w, out)
+        e = ext()
+        xc, wc = x.contiguous(), w.contiguous()
+        if TF32_LINEAR and xc.shape[1] % 4 == 0:
+            out = e.linear_tf32(xc, wc, b, act)
+        else:
+            out = e.linear_f32(xc, wc, b, act)
+        ctx.save_for_backward(xc, wc, out)
         ctx.act = act
+        ctx.params = (w, b)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        e = ext()
         x, w, out = ctx.saved_tensors
-        if ctx.act:
-            dout = dout * torch.where(out > 0, torch.ones_like(out), out + 1)
-        dx = dout @ w if ctx.needs_input_grad[0] else None
-        dw = dout.t() @ x if ctx.needs_input_grad[1] else None
-        db = dout.sum(0) if ctx.needs_input_grad[2] else None
+        wparam, bparam = ctx.params
+        need_b = bparam is not None and ctx.needs_input_grad[2]
+        dz, db = _act_bwd_bias(dout, out, ctx.act, need_b, bparam)
+        dx = e.linear_f32_dgrad(dz, w) if ctx.needs_input_grad[0] else None
+        dw = _dense_wgrad(dz, x, wparam) if ctx.needs_input_grad[1] else None
         return dx, dw, db, None
 
 
@@ -635,5 +812,153 @@ def vae_loss(recon, x, mu, logvar) -> torch.Tensor:
     return _VAELoss.apply(recon, x, mu, logvar)
 
 
+# ----------------------------------------------------------------------------
+# InfoNCE: normalised Gram + diagonal log-softmax, forward in ONE kernel, closed-form backward
+# ----------------------------------------------------------------------------
+INFO_NCE = os.environ.get("FEDB200_INFO_NCE", "1") != "0"
+_NCE_SCRATCH = {}
+
+
 def info_nce_supported(z) -> bool:
-    return False  # vectorised ATen expression for now (one GEMM + softmax); fused kernel is future work
+    return bool(INFO_NCE and z.dim() == 4 and z.dtype == torch.float32 and 1 <= z.shape[2] * z.shape[3] <= ext().info_nce_max_p())
+
+
+def _nce_scratch(device) -> torch.Tensor:
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _NCE_SCRATCH.get(key)
+    if t is None:
+        t = torch.zeros(int(ext().info_nce_scratch_floats()), dtype=torch.float32, device=device)   # self-cleaning afterwards
+        if not torch.cuda.is_current_stream_capturing():
+            _NCE_SCRATCH[key] = t
+    return t
+
+
+class _InfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, zhat):
+        P = z.shape[2] * z.shape[3]
+        Z, Zh = z.reshape(-1, P).contiguous(), zhat.reshape(-1, P).contiguous()
+        loss, coef = ext().info_nce_fwd(Z, Zh, _nce_scratch(z.device))
+        ctx.save_for_backward(Z, Zh, coef)
+        ctx.shape = tuple(z.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        Z, Zh, coef = ctx.saved_tensors
+        dZ, dZh = ext().info_nce_bwd(Z, Zh, coef, gout.reshape(1).float().contiguous())
+        return dZ.view(ctx.shape), dZh.view(ctx.shape)
+
+
+def info_nce(z, zhat) -> torch.Tensor:
+    return _InfoNCE.apply(z, zhat)
+
+
+# ----------------------------------------------------------------------------
+# VAE-CL cost 1: per-(cluster, sample) Gaussian NLL sums, one reduction kernel + one elementwise backward
+# ----------------------------------------------------------------------------
+class _GaussNLLRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mu, s2):
+        B = x.shape[0]
+        xf = x.reshape(B, -1).contiguous()
+        D = xf.shape[1]
+        muf, sf = mu.reshape(-1, D).contiguous(), s2.reshape(-1, D).contiguous()
+        rows = ext().gauss_nll_rows_fwd(xf, muf, sf)
+        ctx.save_for_backward(xf, muf, sf)
+        ctx.shapes = (tuple(mu.shape), tuple(s2.shape))
+        return rows.view(-1, B)
+
+    @staticmethod
+    def backward(ctx, grows):
+        xf, muf, sf = ctx.saved_tensors
+        dmu, ds2 = ext().gauss_nll_rows_bwd(xf, muf, sf, grows.reshape(-1).contiguous())
+        return None, dmu.view(ctx.shapes[0]), ds2.view(ctx.shapes[1])
+
+
+def gauss_nll_rows(x, mu, s2) -> torch.Tensor:
+    """``[Kc, B]`` sums over pixels of ``(x - mu)^2 / (2 s2) + log(2 pi s2) / 2``; ``mu``/``s2``: ``[Kc, B, ...]``."""
+    return _GaussNLLRows.apply(x, mu, s2)
+
+
+# ----------------------------------------------------------------------------
+# 2x2 max pooling and the small direct convolutions of Net / Net1 (SURVEY G4, default classifier)
+# ----------------------------------------------------------------------------
+class _MaxPool2x2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xx = x if (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)) else x.contiguous()
+        y, idx = ext().maxpool2x2_fwd(xx)
+        ctx.save_for_backward(idx)
+        ctx.hw = (x.shape[2], x.shape[3])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return ext().maxpool2x2_bwd(dy, idx, ctx.hw[0], ctx.hw[1])
+
+
+def max_pool2x2(x: torch.Tensor) -> torch.Tensor:
+    return _MaxPool2x2.apply(x)
+
+
+SMALLCONV = os.environ.get("FEDB200_SMALLCONV", "1") != "0"
+
+
+def smallconv_supported(x: torch.Tensor, conv: nn.Module) -> bool:
+    if not SMALLCONV or not isinstance(conv, nn.Conv2d) or isinstance(conv, nn.ConvTranspose2d) or x.dim() != 4:
+        return False
+    if x.dtype != torch.float32 or conv.groups != 1 or conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+        return False
+    if tuple(conv.stride) != (1, 1) or tuple(conv.dilation) != (1, 1) or conv.kernel_size[0] != conv.kernel_size[1]:
+        return False
+    if conv.padding[0] != conv.padding[1]:
+        return False
+    return bool(ext().smallconv_supported(conv.in_channels, conv.out_channels, conv.kernel_size[0]))
+
+
+class _SmallConv(torch.autograd.Function):
+    """``maxpool2x2?(ELU?(conv(x) + b))`` as ONE direct-convolution kernel (NCHW); three kernels in the backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, pad, act, pool):
+        xc, wc = x.contiguous(), weight.contiguous()
+        y, idx = ext().smallconv_fwd(xc, wc, bias, pad, bool(act), bool(pool))
+        ctx.save_for_backward(xc, wc, y, idx)
+        ctx.cfg = (pad, act, pool)
+        ctx.params = (weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        e = ext()
+        xc, wc, y, idx = ctx.saved_tensors
+        pad, act, pool = ctx.cfg
+        wparam, bparam = ctx.params
+        k = wc.shape[2]
+        H, W = xc.shape[2], xc.shape[3]
+        Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+        dz = e.smallconv_unpool_actbwd(dy.contiguous(), y, idx, Ho, Wo, bool(act), bool(pool))
+        dx = e.smallconv_dgrad(dz, wc, H, W, pad) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        need_b = bparam is not None and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            inplace = (_ACC_INTO_GRAD["on"] and getattr(wparam, "grad", None) is not None and wparam.grad.is_contiguous()
+                       and (bparam is None or (getattr(bparam, "grad", None) is not None and bparam.grad.is_contiguous())))
+            if inplace:
+                e.smallconv_wgrad(dz, xc, wparam.grad, bparam.grad if need_b else None, pad)
+            else:
+                dw = torch.zeros_like(wc)
+                db = torch.zeros(wc.shape[0], dtype=torch.float32, device=wc.device) if need_b else None
+                e.smallconv_wgrad(dz, xc, dw, db, pad)
+        return dx, dw, db, None, None, None
+
+
+def small_conv(x, conv: nn.Conv2d, act: bool, pool: bool) -> torch.Tensor:
+    return _SmallConv.apply(x, conv.weight, conv.bias, conv.padding[0], bool(act), bool(pool))
+
+
+def argmax_count(logits: torch.Tensor, labels: torch.Tensor, counter: torch.Tensor) -> None:
+    """counter[0] += #correct, counter[1] += batch size (int64, on the device; evaluation)."""
+    ext().argmax_count(logits.contiguous(), labels, counter)

@@ -86,19 +86,59 @@ def pool_linear(x: torch.Tensor, linear: nn.Linear, window: int = 4) -> torch.Te
 
 def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor:
     """``ELU?(conv(x))`` for the bias-carrying convs / transposed convs of the VAE and CPC nets
-    (/root/reference/src/simple_models.py:249-265, :441-451).  The tcgen05 path (conv + bias + ELU in one kernel) is
-    opt-in in this round (``FEDB200_CONV_ACT=1``, see cuda_ops.conv_act_supported)."""
+    (/root/reference/src/simple_models.py:249-265, :441-451, :478-481, :503-504).  On B200: tcgen05 implicit GEMM with bias +
+    ELU in the epilogue and hand-written backward kernels (cuda_ops._ConvAct); 1x1 convs on odd-sized latent grids run
+    on the dense-layer GEMM kernels, other small convs on the direct-convolution kernel."""
     if _use_fast(x):
         from . import cuda_ops
 
         if cuda_ops.conv_act_supported(x, conv) or cuda_ops.conv_transpose_act_supported(x, conv):
             return cuda_ops.conv_act(x, conv, act)
+        if cuda_ops.conv1x1_supported(x, conv):
+            return cuda_ops.conv1x1_linear(x, conv, act)
+        if cuda_ops.smallconv_supported(x, conv):
+            return cuda_ops.small_conv(x, conv, act, False)
     y = conv(x)
     return F.elu(y) if act else y
 
 
+def conv_act_pool(x: torch.Tensor, conv: nn.Conv2d, act: bool = True, pool: bool = False) -> torch.Tensor:
+    """``max_pool2d?(ELU?(conv(x)), 2, 2)`` — one stage of Net / Net1 / Net2 (/root/reference/src/simple_models.py:19-21,
+    :60-66, :103-110).  Net / Net1 (3..64 channels, 5x5 / 3x3 "valid" convs on 28/10-wide maps): ONE direct-convolution
+    kernel with bias, ELU and the pooling fused; Net2 (padded 3x3, 64..512 channels): tcgen05 conv + NHWC max-pool kernel."""
+    if _use_fast(x):
+        from . import cuda_ops
+
+        if cuda_ops.conv_act_supported(x, conv):
+            y = cuda_ops.conv_act(x, conv, act)
+            return cuda_ops.max_pool2x2(y) if pool else y
+        if cuda_ops.smallconv_supported(x, conv):
+            return cuda_ops.small_conv(x, conv, act, pool)
+    y = conv(x)
+    y = F.elu(y) if act else y
+    return F.max_pool2d(y, 2, 2) if pool else y
+
+
+def max_pool2x2(x: torch.Tensor) -> torch.Tensor:
+    if _use_fast(x) and x.dim() == 4 and x.dtype == torch.float32:
+        from . import cuda_ops
+
+        return cuda_ops.max_pool2x2(x)
+    return F.max_pool2d(x, 2, 2)
+
+
+def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
+    """``avg_pool2d(x, H).squeeze()`` for an H x H map -> ``[N, C]`` (/root/reference/src/simple_models.py:464)."""
+    if _use_fast(x) and x.dim() == 4 and x.dtype == torch.float32:
+        from . import cuda_ops
+
+        return cuda_ops._AvgPoolNHWC.apply(x)
+    return F.avg_pool2d(x, x.shape[2]).reshape(x.shape[0], x.shape[1])
+
+
 def linear_act(x: torch.Tensor, linear: nn.Linear, act: bool = True) -> torch.Tensor:
-    """``ELU?(x @ W^T + b)``; on B200 the skinny GEMM + bias + ELU epilogue is one tcgen05 kernel."""
+    """``ELU?(x @ W^T + b)``; on B200 one hand-written GEMM kernel with the bias + ELU epilogue (true fp32 by default —
+    the reference's nn.Linear precision; FEDB200_TF32_LINEAR=1: tcgen05) and hand-written backward kernels."""
     if _use_fast(x):
         from . import cuda_ops
 

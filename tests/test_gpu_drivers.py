@@ -43,7 +43,8 @@ def test_consensus_admm_bb_resnet_fused():
                       default_batch=32, bb_update=True, graphs=True)
     duals = [l for l in lines if l.startswith("block=[")]
     assert len(duals) == 8 * 3 and any(l.startswith("admm 2 deltas=(") for l in lines)
-    assert eng.coll.name == "fused" and eng.coll.launches == 24 and cuda_ops.launch_count() > before
+    # 8 warm-up launches at engine construction; per block: x0 seed + 3 aggregations + 1 BB update
+    assert eng.coll.name == "fused" and eng.coll.launches - 8 == 8 * 5 and cuda_ops.launch_count() > before
 
 
 def test_fedprox_lbfgs_resnet():
