@@ -264,8 +264,14 @@ def run_ours(args) -> dict:
         task.data = host
         task._loaders.clear()
 
+    step_ev = []          # one CUDA event per step of the device window: shows whether a slow window is uniform or a hiccup
+
     def hook(e: Engine):
         n = e.steps_done
+        if first_d <= n <= last_d:
+            evn = torch.cuda.Event(enable_timing=True)
+            evn.record()
+            step_ev.append(evn)
         if n == 1 and st["t_first_step"] is None:
             torch.cuda.synchronize(dev)
             st["t_first_step"] = time.perf_counter() - T_PROCESS_START
@@ -320,6 +326,10 @@ def run_ours(args) -> dict:
         "gpu_launches": st["d"].get("launches"),
         "time_to_first_step_s": st["t_first_step"], "build_s": t_built - T_PROCESS_START,
     }
+    if len(step_ev) > 1:
+        per = [round(a.elapsed_time(b), 3) for a, b in zip(step_ev[:-1], step_ev[1:])]
+        out["config"]["per_step_ms"] = {"min": min(per), "median": statistics.median(per), "max": max(per),
+                                        "note": "CUDA event after every step of the timed window (the step that contains the aggregation and its host read is the max)"}
     if not args.no_e2e:
         ms_e = _max_over_ranks(ev_e[0].elapsed_time(ev_e[1]), dev)
         wall_e = _max_over_ranks((st["e"]["t1"] - st["e"]["t0"]) * 1e3, dev)

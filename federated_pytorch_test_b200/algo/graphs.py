@@ -39,6 +39,62 @@ def _grad_sink():
     return contextlib.nullcontext()
 
 
+def capture_graph(stream, body):
+    """Capture ``body()`` into a new CUDA graph on ``stream``; returns ``(graph, body's return value)``.
+
+    A CUDAGraph that is garbage (e.g. the graphs of a previous Engine, kept alive by a reference cycle) must not be
+    finalised while a capture is in progress: cudaGraphExecDestroy is "not permitted when stream is capturing" and
+    invalidates the capture (measured: profiles/r2_call2).  torch.cuda.graph no longer collects by itself, so: collect
+    first, keep the cyclic collector off during the capture."""
+    import gc
+
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(g, stream=stream):
+            out = body()
+    finally:
+        if was_enabled:
+            gc.enable()
+    return g, out
+
+
+class GraphedEval:
+    """Evaluation forward of one replica at one batch shape as a CUDA graph: the reference evaluates all K
+    models on 10 000 test images after EVERY aggregation round (79 batches x K x 360 rounds for ResNet18,
+    /root/reference/src/federated_multi.py:108-121) with ~70 eager launches per batch.  Captured here: forward (train-mode
+    BatchNorm statistics included, Q4) + the fused argmax / compare / count kernel; the counter lives on the device."""
+
+    WARMUP = 2
+
+    def __init__(self, net, batch, counter: torch.Tensor, device):
+        self.net, self.counter = net, counter
+        self.static = [t.clone() for t in batch]
+        self.graph = None
+        self.calls = 0
+        self.stream = torch.cuda.Stream(device=device)
+
+    def _body(self):
+        logits = self.net(self.static[0])
+        cuda_ops.argmax_count(logits, self.static[1], self.counter)
+        return None
+
+    @torch.no_grad()
+    def run(self, batch) -> None:
+        for dst, src in zip(self.static, batch):
+            dst.copy_(src, non_blocking=True)
+        self.calls += 1
+        if self.graph is None:
+            if self.calls <= self.WARMUP:
+                self._body()
+                return
+            self.graph, _ = capture_graph(self.stream, self._body)
+        self.graph.replay()
+
+
 class GraphedAdamStep:
     WARMUP = 3
 
@@ -72,24 +128,8 @@ class GraphedAdamStep:
                 rho_key, self.visit.lambda1, self.visit.lambda2)
 
     def _capture(self) -> None:
-        import gc
-
         before = cuda_ops.launch_count()
-        g = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        # A CUDAGraph that is garbage (e.g. the graphs of a previous Engine, kept alive by a reference cycle) must not be
-        # finalised while a capture is in progress: cudaGraphExecDestroy is "not permitted when stream is capturing" and
-        # invalidates the capture (measured: profiles/r2_call2).  torch.cuda.graph no longer collects by itself.
-        gc.collect()
-        was_enabled = gc.isenabled()
-        gc.disable()
-        try:
-            with torch.cuda.graph(g, stream=self.stream):
-                self.loss_out = self._body()
-        finally:
-            if was_enabled:
-                gc.enable()
-        self.graph = g
+        self.graph, self.loss_out = capture_graph(self.stream, self._body)
         self.kernels_per_replay = cuda_ops.launch_count() - before
 
     def run(self, batch, pen) -> torch.Tensor:

@@ -80,6 +80,8 @@ class ClassifierTask(Task):
         self.channels_last = bool(cfg.fast and topo.device.type == "cuda" and name.startswith("ResNet"))
         self._loaders: Dict[int, ShardLoader] = {}
         self._test_loaders: Dict[int, ShardLoader] = {}
+        self._eval_graphs: Dict = {}
+        self._eval_counters: Dict[int, torch.Tensor] = {}
         probe = self.factory()
         self.blocks = probe.train_order_block_ids()
         self.linear_ids = probe.linear_layer_ids()
@@ -172,11 +174,22 @@ class ClassifierTask(Task):
         read per replica.
         """
         fused = self.topo.device.type == "cuda" and FX.fast_path_enabled()
+        graphed = fused and bool(getattr(self.cfg, "graphs", False))
         counters = []
         for rep in reps:
             net = rep.nets["net"]
-            counter = torch.zeros(2, dtype=torch.int64, device=rep.device)      # [#correct, #seen], stays on the device
+            counter = self._eval_counters.setdefault(rep.ck, torch.zeros(2, dtype=torch.int64, device=rep.device))
+            counter.zero_()                                                      # [#correct, #seen], stays on the device
             for x, y in self.test_loader(rep.ck):
+                if graphed:
+                    from ..algo.graphs import GraphedEval
+
+                    key = (rep.ck, tuple(x.shape))
+                    ge = self._eval_graphs.get(key)
+                    if ge is None:
+                        ge = self._eval_graphs[key] = GraphedEval(net, (x, y), counter, rep.device)
+                    ge.run((x, y))                                               # forward + argmax/compare/count: one graph launch
+                    continue
                 logits = net(x)
                 if fused:
                     from ..ops import cuda_ops

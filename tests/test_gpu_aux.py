@@ -167,19 +167,24 @@ def test_small_direct_conv_forward_backward(B, Ci, H, Co, k, pad, act, pool):
     assert rel_err(gx, rx) < 1e-4 and rel_err(gw, rw) < 1e-4 and rel_err(gb, rb) < 1e-4
 
 
-def _twin_grads(factory, inputs, loss_fn, tol):
-    """Same module twice; one stepped on the fast path, one on the ATen path; compares loss and every parameter gradient."""
+def _twin_grads(factory, inputs, loss_fn, tol, ref_double=False):
+    """Same module twice; one stepped on the fast path, one on the ATen path (optionally in fp64: cuDNN's fp32 convolutions
+    may still multiply in TF32); compares loss and every parameter gradient."""
     torch.manual_seed(0)
     a = factory().to(DEV)
     b = factory().to(DEV)
     b.load_state_dict(a.state_dict())
+    ref_inputs = inputs
+    if ref_double:
+        b = b.double()
+        ref_inputs = tuple(t.double() if t.is_floating_point() else t for t in inputs)
     torch.manual_seed(1)
     FX.set_fast_path(True)
     la = loss_fn(a, *inputs)
     la.backward()
     torch.manual_seed(1)
     FX.set_fast_path(False)
-    lb = loss_fn(b, *inputs)
+    lb = loss_fn(b, *ref_inputs)
     lb.backward()
     FX.set_fast_path(True)
     assert float(la) == pytest.approx(float(lb), rel=tol)
@@ -190,8 +195,9 @@ def _twin_grads(factory, inputs, loss_fn, tol):
 def test_net_and_net2_fast_path_match_aten():
     x = torch.randn(32, 3, 32, 32, device=DEV)
     y = torch.randint(0, 10, (32,), device=DEV)
-    _twin_grads(models.Net, (x, y), lambda m, xx, yy: losses.cross_entropy(m(xx), yy), 1e-4)
-    _twin_grads(models.Net1, (x, y), lambda m, xx, yy: losses.cross_entropy(m(xx), yy), 1e-4)
+    # Net / Net1 run entirely in true fp32 on the fast path: compare against an fp64 oracle
+    _twin_grads(models.Net, (x, y), lambda m, xx, yy: losses.cross_entropy(m(xx), yy), 1e-4, ref_double=True)
+    _twin_grads(models.Net1, (x, y), lambda m, xx, yy: losses.cross_entropy(m(xx), yy), 1e-4, ref_double=True)
     _twin_grads(models.Net2, (x, y), lambda m, xx, yy: losses.cross_entropy(m(xx), yy), 5e-3)      # tf32 convs
 
 
