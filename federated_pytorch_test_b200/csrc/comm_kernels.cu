@@ -123,6 +123,32 @@ __device__ __forceinline__ void cta_peer_barrier(uint32_t* const* ctrl, int worl
   __syncthreads();
 }
 
+// sum over all K workers of x_k (+ y_k / rho-scaled for ADMM) at float4 index `off`: one in-switch reduction or K peer loads
+__device__ __forceinline__ float4 gather_v4(const CommArgs& a, size_t off, float rho, bool use_mc) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (use_mc) {
+    acc = multimem_ld_reduce_v4(a.mc_x + off);
+    if (a.mode == 2) {
+      const float4 ys = multimem_ld_reduce_v4(a.mc_y + off);
+      acc.x = fmaf(rho, acc.x, ys.x); acc.y = fmaf(rho, acc.y, ys.y);
+      acc.z = fmaf(rho, acc.z, ys.z); acc.w = fmaf(rho, acc.w, ys.w);
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < a.K; ++k) {
+      const float4 xv = ld_sys_v4(a.x[k] + off);
+      if (a.mode == 2) {
+        const float4 yv = ld_sys_v4(a.y[k] + off);
+        acc.x += fmaf(rho, xv.x, yv.x); acc.y += fmaf(rho, xv.y, yv.y);
+        acc.z += fmaf(rho, xv.z, yv.z); acc.w += fmaf(rho, xv.w, yv.w);
+      } else {
+        acc.x += xv.x; acc.y += xv.y; acc.z += xv.z; acc.w += xv.w;
+      }
+    }
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(COMM_THREADS, 1) block_reduce_kernel(const CommArgs a) {
   __shared__ float sm[32];
   __shared__ int s_abort;
@@ -148,42 +174,36 @@ __global__ void __launch_bounds__(COMM_THREADS, 1) block_reduce_kernel(const Com
   {
     const int lo = my_slice * chunk4;
     const int hi = min(n4, lo + chunk4);
-    for (int i = lo + t0; i < hi; i += stride) {
-      const size_t off = 4 * size_t(i);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (use_mc) {
-        acc = multimem_ld_reduce_v4(a.mc_x + off);
-        if (a.mode == 2) {
-          const float4 ys = multimem_ld_reduce_v4(a.mc_y + off);
-          acc.x = fmaf(rho, acc.x, ys.x); acc.y = fmaf(rho, acc.y, ys.y);
-          acc.z = fmaf(rho, acc.z, ys.z); acc.w = fmaf(rho, acc.w, ys.w);
+    // two elements per thread and iteration: their (remote) loads are issued back to back, so twice as many bytes are in
+    // flight per thread — the pass is bound by NVLink round trips, not by issue slots
+    for (int i = lo + t0; i < hi; i += 2 * stride) {
+      const int i1 = i + stride;
+      const bool has1 = i1 < hi;
+      const size_t off0 = 4 * size_t(i), off1 = 4 * size_t(has1 ? i1 : i);
+      float4 accs[2];
+      accs[0] = gather_v4(a, off0, rho, use_mc);
+      accs[1] = has1 ? gather_v4(a, off1, rho, use_mc) : accs[0];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has1) break;
+        const size_t off = u == 0 ? off0 : off1;
+        const float4 acc = accs[u];
+        const float4 zn = make_float4(acc.x * inv_scale, acc.y * inv_scale, acc.z * inv_scale, acc.w * inv_scale);
+        if (!(a.two_shot && a.mode == 0)) {       // two-shot FedAvg takes both from the finished weights in pass 2
+          const float4 zo = *reinterpret_cast<const float4*>(a.z + off);
+          const float dx = zo.x - zn.x, dy = zo.y - zn.y, dz = zo.z - zn.z, dw = zo.w - zn.w;
+          dual = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, dual))));
+          if (!(isfinite(zn.x) && isfinite(zn.y) && isfinite(zn.z) && isfinite(zn.w))) bad += 1.f;
         }
-      } else {
-#pragma unroll 4
-        for (int k = 0; k < a.K; ++k) {
-          const float4 xv = ld_sys_v4(a.x[k] + off);
-          if (a.mode == 2) {
-            const float4 yv = ld_sys_v4(a.y[k] + off);
-            acc.x += fmaf(rho, xv.x, yv.x); acc.y += fmaf(rho, xv.y, yv.y);
-            acc.z += fmaf(rho, xv.z, yv.z); acc.w += fmaf(rho, xv.w, yv.w);
-          } else {
-            acc.x += xv.x; acc.y += xv.y; acc.z += xv.z; acc.w += xv.w;
-          }
+        if (!a.two_shot) {
+          *reinterpret_cast<float4*>(a.z + off) = zn;
+        } else if (a.mode == 0) {                 // broadcast the averaged weights into every rank's replica
+          if (a.mc_x != nullptr) multimem_st_v4(a.mc_x + off, zn);
+          else for (int p = 0; p < a.world; ++p) st_sys_v4(a.xw[p] + off, zn);
+        } else {                                   // broadcast the consensus vector
+          if (a.mc_z != nullptr) multimem_st_v4(a.mc_z + off, zn);
+          else for (int p = 0; p < a.world; ++p) st_sys_v4(a.zw[p] + off, zn);
         }
-      }
-      const float4 zo = *reinterpret_cast<const float4*>(a.z + off);
-      const float4 zn = make_float4(acc.x * inv_scale, acc.y * inv_scale, acc.z * inv_scale, acc.w * inv_scale);
-      const float dx = zo.x - zn.x, dy = zo.y - zn.y, dz = zo.z - zn.z, dw = zo.w - zn.w;
-      dual = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, dual))));
-      if (!(isfinite(zn.x) && isfinite(zn.y) && isfinite(zn.z) && isfinite(zn.w))) bad += 1.f;
-      if (!a.two_shot) {
-        *reinterpret_cast<float4*>(a.z + off) = zn;
-      } else if (a.mode == 0) {                 // broadcast the averaged weights into every rank's replica
-        if (a.mc_x != nullptr) multimem_st_v4(a.mc_x + off, zn);
-        else for (int p = 0; p < a.world; ++p) st_sys_v4(a.xw[p] + off, zn);
-      } else {                                   // broadcast the consensus vector
-        if (a.mc_z != nullptr) multimem_st_v4(a.mc_z + off, zn);
-        else for (int p = 0; p < a.world; ++p) st_sys_v4(a.zw[p] + off, zn);
       }
     }
   }
@@ -203,7 +223,7 @@ __global__ void __launch_bounds__(COMM_THREADS, 1) block_reduce_kernel(const Com
     }
     const float zn = acc * inv_scale;
     const float d = a.z[i] - zn;
-    if (!a.two_shot || a.rank == 0) dual = fmaf(d, d, dual);     // two-shot: the dual parts are summed over ranks
+    if (!a.two_shot || a.mode == 0 || a.rank == 0) dual = fmaf(d, d, dual);     // two-shot FedProx/ADMM: the dual parts are summed over ranks
     if (!isfinite(zn)) bad += 1.f;
     a.z[i] = zn;
   }
@@ -222,8 +242,13 @@ __global__ void __launch_bounds__(COMM_THREADS, 1) block_reduce_kernel(const Com
     for (int i = lo + t0; i < hi; i += stride) {
       const size_t off = 4 * size_t(i);
       if (a.mode == 0) {
-        if (a.two_shot) {                        // weights already hold the average: keep a copy as next round's z_old
-          *reinterpret_cast<float4*>(a.z + off) = ld_sys_v4(a.xl[0] + off);
+        if (a.two_shot) {                        // weights already hold the average: keep a copy as next round's z_old,
+          const float4 zn = ld_sys_v4(a.xl[0] + off);          // and take the dual residual + NaN check from it (the full vector
+          const float4 zo = *reinterpret_cast<const float4*>(a.z + off);   // is local now: no cross-rank sum needed)
+          const float dx = zo.x - zn.x, dy = zo.y - zn.y, dz = zo.z - zn.z, dw = zo.w - zn.w;
+          dual = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, dual))));
+          if (!(isfinite(zn.x) && isfinite(zn.y) && isfinite(zn.z) && isfinite(zn.w))) bad += 1.f;
+          *reinterpret_cast<float4*>(a.z + off) = zn;
         } else {
           const float4 zv = *reinterpret_cast<const float4*>(a.z + off);
           for (int j = 0; j < a.n_local; ++j) *reinterpret_cast<float4*>(a.xl[j] + off) = zv;
@@ -300,7 +325,7 @@ __global__ void __launch_bounds__(COMM_THREADS, 1) block_reduce_kernel(const Com
   }
   __syncthreads();
   float dual_sq = s_vals[0], primal = s_vals[1], nonfinite = s_vals[2];
-  if (a.world > 1) {
+  if (a.world > 1 && a.mode != 0) {          // FedAvg: every rank already holds the complete dual residual and NaN count
     if (threadIdx.x < a.world) {
       float* pay = reinterpret_cast<float*>(a.ctrl[threadIdx.x] + PAD_PAYLOAD) + 4 * a.rank;
       st_sys_f32(pay + 0, dual_sq);
@@ -372,8 +397,13 @@ void block_reduce_launch(const CommArgs& args_in, cudaStream_t s) {
   int grid = want < 1 ? 1 : (want > cap ? cap : want);
   if (args.timeout_cycles <= 0) args.timeout_cycles = 240000000000LL;   // ~2 min at 2 GHz
   void* kargs[] = {(void*)&args};
-  // cooperative launch: all CTAs are co-resident, which the per-CTA cross-rank barriers rely on
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)block_reduce_kernel, dim3(grid), dim3(COMM_THREADS), kargs, 0, s);
+  // Plain launch: a CTA only ever waits for the SAME-numbered CTA of its peers (never for another CTA of its own grid), so
+  // co-residency of the grid is not required; a cooperative launch costs ~5 us more per aggregation (measured,
+  // profiles/r2_collective.md).  FEDB200_COMM_COOP=1 restores it (A/B runs).
+  static const int coop = env_int_c("FEDB200_COMM_COOP", 0);
+  cudaError_t e;
+  if (coop) e = cudaLaunchCooperativeKernel((void*)block_reduce_kernel, dim3(grid), dim3(COMM_THREADS), kargs, 0, s);
+  else e = cudaLaunchKernel((void*)block_reduce_kernel, dim3(grid), dim3(COMM_THREADS), kargs, 0, s);
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: block_reduce launch: ") + cudaGetErrorString(e));
   count_launch();
 }
