@@ -429,7 +429,8 @@ class Engine:
         aggregation latency and NVLink bus bandwidth (nccl-tests convention: 2 (W-1)/W * bytes / time)."""
         now = time.perf_counter()
         mark = self._round_mark
-        summ = self.timers.summary(reduce_max=False)
+        # only the (few) aggregate / eval events are resolved here — the GPU is idle while the host is in this function
+        summ = self.timers.summary(reduce_max=False, names=("aggregate", "eval"))
         out: Dict[str, float] = {}
         dt = max(now - mark["t"], 1e-9)
         out["images_per_s"] = (self.images_seen - mark["images"]) / dt

@@ -618,11 +618,12 @@ void conv_wgrad_tf32(const float* x, const float* dy, float* dw, int NB, int H, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  // split the pixel range until ~two waves of CTAs exist, but keep >= 4 k-blocks per CTA (prologue + red.add epilogue)
+  // Split the pixel range until ~ONE wave of CTAs exists (every split adds a full |dW| of reduce-add traffic in the
+  // epilogue), keeping >= 4 k-blocks per CTA (prologue + epilogue amortisation).
   const int base = p.g_units * p.co_tiles;
   int splits = env_int("FEDB200_WGRAD_SPLITS", 0);
   if (splits <= 0) {
-    splits = std::max(1, (2 * sms) / base);
+    splits = std::max(1, sms / base);
     splits = std::min(splits, std::max(1, p.kb_total / 4));
   }
   splits = std::min(splits, p.kb_total);
@@ -630,14 +631,26 @@ void conv_wgrad_tf32(const float* x, const float* dy, float* dw, int NB, int H, 
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;       // no empty slices
   const CUtensorMap tx = make_tmap_pixels(x, NB, H, W, C_x, p.NBX, p.HB, p.WB, stride);
   const CUtensorMap tdy = make_tmap_pixels(dy, NB, H_out, W_out, C_out, p.NBX, p.HB, p.WB, 1);
-  const int smem = p.stages * p.stage_bytes + (2 * WG_MAX_STAGES + 2) * 8 + 16 + 1024;
+  // dW viewed as a [C_out] x [taps * C_w] matrix for the bulk reduce-add epilogue: 32 x 32 boxes, plain row-major
+  p.tma_red = ((C_w & 3) == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0 && env_int("FEDB200_WGRAD_TMA_RED", 1) != 0) ? 1 : 0;
+  CUtensorMap tdw = tx;
+  if (p.tma_red) {
+    cuuint64_t dims[2] = {cuuint64_t(p.taps) * C_w, cuuint64_t(C_out)};
+    cuuint64_t strides[1] = {cuuint64_t(p.taps) * C_w * sizeof(float)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    check_cu(encode_fn()(&tdw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+             "cuTensorMapEncodeTiled(dw)");
+  }
+  const int smem = p.stages * p.stage_bytes + 4 * 4096 + (2 * WG_MAX_STAGES + 2) * 8 + 16 + 1024;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: cudaFuncSetAttribute(wgrad): ") + cudaGetErrorString(e));
     configured = 227 * 1024;
   }
-  cudaError_t e = launch_pdl(wgrad_tf32_kernel, dim3(base * splits), dim3(WG_THREADS), size_t(smem), stream, tx, tdy, p);
+  cudaError_t e = launch_pdl(wgrad_tf32_kernel, dim3(base * splits), dim3(WG_THREADS), size_t(smem), stream, tx, tdy, tdw, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: wgrad launch: ") + cudaGetErrorString(e));
   count_launch();
 }

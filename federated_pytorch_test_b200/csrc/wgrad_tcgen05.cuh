@@ -50,6 +50,7 @@ struct WgradParams {
   int stages, stage_bytes;
   uint32_t tmem_cols;
   float* dw;            // [Co, taps, Cw]
+  int tma_red;          // 1: epilogue = shared-memory staging + bulk tensor reduce-add (needs (taps * Cw) % 4 == 0)
 };
 
 // MN-major tf32 operand, SWIZZLE_128B_BASE32B (layout type 1): start address, LBO = distance between 32-element
@@ -72,11 +73,13 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy, const WgradParams p) {
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                  const __grid_constant__ CUtensorMap tmap_dw, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  float* stage_out = reinterpret_cast<float*>(smem + p.stages * p.stage_bytes);      // 4 warps x [32 co][32 ci] fp32
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes + 4 * 4096);
   uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
   uint64_t* t_full = empty_bar + WG_MAX_STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(t_full + 1);
@@ -101,6 +104,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_dy);
+    if (p.tma_red) tma_prefetch_desc(&tmap_dw);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -178,22 +182,44 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       umma_commit(t_full);
     }
   } else {
-    // ===================== epilogue (warps 2..5): TMEM -> red.add into dW =====================
+    // ===================== epilogue (warps 2..5): TMEM -> dW (accumulated) =====================
+    // Partial sums of every CTA are ADDED into dW.  Per-element red.global.add is bound by the L2 atomic units
+    // (~145 elements / clock chip-wide, measured: layer4 with 8 pixel splits = 18.9 M reds = 69 us of a 70 us kernel,
+    // profiles/r2_wgrad.md), so the default path transposes each 32 (ci) x 32 (co) chunk through shared memory into
+    // [co][ci] rows — the memory order of dW — and hands it to ONE bulk tensor reduce-add (cp.reduce.async.bulk.tensor,
+    // 128-bit wide in L2, no LSU instructions).  Lanes outside the tensor (ci >= Cw, box >= nbox_a) contribute zeros;
+    // rows / columns outside dW are clipped by the TMA unit.
     const int q = warp & 3;
     const uint32_t ncols = uint32_t(p.nb * 32);
+    float* my_stage = stage_out + (warp - 2) * 1024;
     if (kb1 > kb0) {
       mbar_wait(t_full, 0);
       tc_fence_after();
       for (int g = 0; g < ngroups; ++g) {
         const int b = 4 * (g0 + g) + q;                 // this warp's box: 32 channels of one tap
         const int tap = b / p.nbox_ci;
-        const int ci = (b - tap * p.nbox_ci) * 32 + lane;
-        const bool row_ok = b < p.nbox_a && ci < p.Cw;
+        const int cg = b - tap * p.nbox_ci;
+        const int ci = cg * 32 + lane;
+        const bool box_ok = b < p.nbox_a;               // warp-uniform
+        const bool row_ok = box_ok && ci < p.Cw;
         for (uint32_t c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(g) * ncols + c0, v);
           tmem_ld_wait();
-          if (row_ok) {
+          if (p.tma_red) {
+            if (box_ok && co0 + int(c0) < p.Co) {
+              if (lane == 0) tma_store_wait_read();      // the previous chunk's reduce has drained the staging tile
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) my_stage[j * 32 + lane] = row_ok ? __uint_as_float(v[j]) : 0.f;
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_reduce_add_2d(&tmap_dw, my_stage, tap * p.Cw + cg * 32, co0 + int(c0));
+                tma_store_commit();
+              }
+            }
+          } else if (row_ok) {
             float* dst = p.dw + (size_t(co0 + c0) * p.taps + tap) * p.Cw + ci;
             const size_t co_pitch = size_t(p.taps) * p.Cw;
 #pragma unroll
@@ -202,6 +228,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
+      if (p.tma_red && lane == 0) tma_store_wait_read();   // shared memory must outlive the last bulk reduce's read
     }
     tc_fence_before();
   }

@@ -176,6 +176,8 @@ class ShardLoader:
         self.gen = torch.Generator().manual_seed(seed)
         self.channels_last = channels_last
         self.with_labels = with_labels
+        self.prefetch_order = True     # see _device_order(); a loader abandoned mid-epoch simply never prefetches
+        self._next_order = None
         self.host_resident = not images.is_cuda and self.device.type == "cuda"
         self._assembler = None
         if self.host_resident:
@@ -196,14 +198,30 @@ class ShardLoader:
             return self.index
         return self.index[torch.randperm(len(self.index), generator=self.gen)]
 
-    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    def _device_order(self) -> torch.Tensor:
+        """This epoch's sample order on the dataset's device.  Shuffled loaders draw the NEXT epoch's permutation right
+        after handing out the last batch of the current one (while the GPU is still busy with it), so that the start of
+        a round — the host's critical path after an aggregation — costs nothing.  The generator is consumed in the
+        same sequence as without the prefetch (one ``randperm`` per epoch)."""
+        nxt = getattr(self, "_next_order", None)
+        self._next_order = None
+        if nxt is not None:
+            return nxt
         order = self._order()
+        if self.images.is_cuda:
+            return order.pin_memory().to(self.images.device, non_blocking=True) if torch.cuda.is_available() else order.to(self.images.device)
+        return order
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         nb = len(self)
         if self._assembler is not None:
-            yield from self._iter_host(order, nb)
+            yield from self._iter_host(self._order(), nb)
             return
-        dev_order = order.to(self.images.device)
+        dev_order = self._device_order()
         for b in range(nb):
+            if b == nb - 1 and self.shuffle and self.prefetch_order:
+                self._next_order = None
+                self._next_order = self._device_order()
             idx = dev_order[b * self.batch_size:(b + 1) * self.batch_size]
             x = normalize_batch(self.images.index_select(0, idx), self.mean, self.std, self.channels_last)
             y = self.labels.index_select(0, idx)

@@ -96,7 +96,8 @@ def save_resume(path: str, engine, position: Dict) -> str:
     loaders = {}
     for ck, ld in getattr(engine.task, "_loaders", {}).items():
         if hasattr(ld, "gen"):
-            loaders[ck] = ld.gen.get_state()
+            nxt = getattr(ld, "_next_order", None)        # the next epoch's permutation may already have been drawn (prefetch)
+            loaders[ck] = {"gen": ld.gen.get_state(), "next_order": None if nxt is None else nxt.detach().cpu().clone()}
     rec = {
         "position": dict(position),
         "strategy": engine.strategy.name,
@@ -141,7 +142,9 @@ def load_resume(path: str, engine) -> Dict:
     for ck, state in (rec.get("loader_rng") or {}).items():
         ld = engine.task.loader(ck) if hasattr(engine.task, "loader") else None
         if ld is not None and hasattr(ld, "gen"):
-            ld.gen.set_state(state)
+            ld.gen.set_state(state["gen"])
+            nxt = state.get("next_order")
+            ld._next_order = None if nxt is None else nxt.to(ld.images.device)
     cnt = rec.get("counters") or {}
     engine.images_seen = int(cnt.get("images_seen", 0))
     engine.steps_done = int(cnt.get("steps_done", 0))

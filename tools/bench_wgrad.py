@@ -49,7 +49,7 @@ def main():
         err = float((buf.permute(0, 3, 1, 2).double() - ref).abs().max() / ref.abs().max())
         t_c = timed(cudnn)
         t_o = timed(ours)
-        print("%-8s %10.1f %10.1f %9.1f %8.1f%% %8.1e" % (name, t_o, t_c, gf / t_o * 1e-3, 100 * gf / t_o * 1e-3 / PEAK_TF32, err), flush=True)
+        print("%-8s %10.1f %10.1f %9.1f %8.1f%% %8.1e" % (name, t_o, t_c, gf / t_o * 1e3, 100 * gf / t_o * 1e3 / PEAK_TF32, err), flush=True)
 
 
 if __name__ == "__main__":

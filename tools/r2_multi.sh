@@ -30,5 +30,7 @@ PY
 echo "=== bench N=$N consensus --bb" >> $LOG
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 20 --warmup 5 --driver consensus --bb --no-e2e --no-collective-table 2>&1 | tail -1 | cut -c1-500 >> $LOG
 echo "=== bench N=$N --impl nccl (ATen model + NCCL all-reduce: the baseline, not the product)" >> $LOG
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --steps 20 --warmup 5 --impl nccl --no-e2e --no-collective-table 2>&1 | tail -1 | cut -c1-400 >> $LOG
+NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --steps 20 --warmup 5 --impl nccl --no-e2e --no-collective-table > gpurun_out/nccl_n$N.out 2>&1
+grep -i -m3 "nvls" gpurun_out/nccl_n$N.out | cut -c1-200 >> $LOG
+grep '^{' gpurun_out/nccl_n$N.out | tail -1 | cut -c1-400 >> $LOG
 echo "=== done" >> $LOG
