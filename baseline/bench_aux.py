@@ -52,14 +52,15 @@ def run_aux_bench(args) -> dict:
     ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
     st = {}
     sampler = ClockSampler(dev.index or 0) if topo.is_root else None
+    if sampler:
+        sampler.start()          # early: NVML start-up stalls launches on every GPU of the box (see bench.py)
 
     def hook(e: Engine):
         n = e.steps_done
         if n == first:
             topo.barrier()
             torch.cuda.synchronize(dev)
-            if sampler:
-                sampler.start()
+            st["smi0"] = sampler.mark() if sampler else 0
             st.update(l0=cuda_ops.launch_count(), g0=e.graph_kernel_launches, a0=e.aggregations_done, t0=time.perf_counter())
             ev[0].record()
         elif n == last:
@@ -67,11 +68,13 @@ def run_aux_bench(args) -> dict:
             torch.cuda.synchronize(dev)
             topo.barrier()
             st.update(t1=time.perf_counter(), launches=(cuda_ops.launch_count() - st["l0"]) + (e.graph_kernel_launches - st["g0"]),
-                      aggs=e.aggregations_done - st["a0"], clocks=sampler.stop() if sampler else None)
+                      aggs=e.aggregations_done - st["a0"], clocks=sampler.window(st["smi0"], sampler.mark()) if sampler else None)
             e.stop_requested = True
 
     eng.step_hook = hook
     eng.run()
+    if sampler:
+        sampler.stop()
     ms = _max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
     wall = _max_over_ranks((st["t1"] - st["t0"]) * 1e3, dev)
     out = {

@@ -197,9 +197,12 @@ def run_reference_bench(gpus: int, steps: int, warmup: int, driver: str = "feder
     from bench import ClockSampler  # same clock sampling as the product arm
 
     sampler = ClockSampler(0)
+    sampler.start()      # early (NVML start-up must not fall into the timed region); the window is marked by sample index
+    marks = {}
     res = run_reference_script(script, consts, steps=timed * gpus, warmup=first, workdir="/tmp/fedref_run",
-                               on_timed_start=sampler.start, optimizer=optimizer)   # clocks sampled during the timed region only
-    clocks = sampler.stop()
+                               on_timed_start=lambda: marks.setdefault("i0", sampler.mark()), optimizer=optimizer)
+    clocks = sampler.window(marks.get("i0", 0), sampler.mark())
+    sampler.stop()
     ms = max(res.get("device_ms", 0.0), res.get("wall_ms", 0.0))
     images = 128 * gpus * timed
     value = images / (ms / 1e3)

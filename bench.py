@@ -72,14 +72,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self) -> int:
+        """Index of the next sample: ``window(mark_at_open, mark_at_close)`` summarises only what was sampled in between."""
+        return len(self.rows)
+
+    def window(self, i0: int, i1: int) -> dict:
+        return self._summarise(self.rows[max(0, i0 - 1): i1 + 1])      # include the samples that bracket the window
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        return self._summarise(self.rows)
+
+    def _summarise(self, rows) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -222,7 +234,12 @@ def run_ours(args) -> dict:
     slots = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     slot_ev = [torch.cuda.Event(), torch.cuda.Event()]
     pending = []
-    sampler = {"d": ClockSampler(dev.index or 0) if topo.is_root else None, "e": ClockSampler(dev.index or 0) if topo.is_root else None}
+    # ONE nvidia-smi sampler for the whole run, started before the first step: its start-up (NVML attaches to every GPU of the
+    # box) stalls CUDA launches of ALL ranks for tens of ms on an 8-GPU node — inside a 50 ms window that contains a cross-rank
+    # aggregation this was measured as a 30 ms "step" (profiles/r2_scaling.md).  The windows only mark sample indices.
+    smi = ClockSampler(dev.index or 0) if (topo.is_root and os.environ.get("FEDB200_BENCH_NO_SMI", "0") != "1") else None
+    if smi:
+        smi.start()
 
     import gc
 
@@ -234,8 +251,7 @@ def run_ours(args) -> dict:
         gc.disable()      # a cyclic-GC pause (~10 ms with this heap) inside a 50 ms window is 20 % noise; re-enabled at close
         topo.barrier()
         torch.cuda.synchronize(dev)
-        if sampler[tag]:
-            sampler[tag].start()
+        st[tag]["smi0"] = smi.mark() if smi else 0
         st[tag].update(l0=cuda_ops.launch_count(), g0=getattr(eng, "graph_kernel_launches", 0), a0=eng.aggregations_done,
                        t0=time.perf_counter())
         st["wait"] = 0.0
@@ -251,7 +267,7 @@ def run_ours(args) -> dict:
         s["launches"] = (cuda_ops.launch_count() - s["l0"]) + (getattr(eng, "graph_kernel_launches", 0) - s["g0"])
         s["aggregations"] = eng.aggregations_done - s["a0"]
         s["wait_ms"] = st["wait"] * 1e3
-        s["clocks"] = sampler[tag].stop() if sampler[tag] else None
+        s["clocks"] = smi.window(s["smi0"], smi.mark()) if smi else None
 
     def swap_to_host_loaders():
         """From the next round on, batches come from pinned host memory through the native batch assembler."""
@@ -264,14 +280,19 @@ def run_ours(args) -> dict:
         task.data = host
         task._loaders.clear()
 
-    step_ev = []          # one CUDA event per step of the device window: shows whether a slow window is uniform or a hiccup
+    step_ev = {"d": [], "e": []}   # one CUDA event per step of a timed window: is a slow window uniform, or one long step?
+
+    def stamp(tag):
+        evn = torch.cuda.Event(enable_timing=True)
+        evn.record()
+        step_ev[tag].append(evn)
 
     def hook(e: Engine):
         n = e.steps_done
-        if first_d <= n <= last_d:
-            evn = torch.cuda.Event(enable_timing=True)
-            evn.record()
-            step_ev.append(evn)
+        if first_d < n <= last_d:
+            stamp("d")
+        elif (not args.no_e2e) and first_e < n <= last_e:
+            stamp("e")
         if n == 1 and st["t_first_step"] is None:
             torch.cuda.synchronize(dev)
             st["t_first_step"] = time.perf_counter() - T_PROCESS_START
@@ -326,10 +347,18 @@ def run_ours(args) -> dict:
         "gpu_launches": st["d"].get("launches"),
         "time_to_first_step_s": st["t_first_step"], "build_s": t_built - T_PROCESS_START,
     }
-    if len(step_ev) > 1:
-        per = [round(a.elapsed_time(b), 3) for a, b in zip(step_ev[:-1], step_ev[1:])]
-        out["config"]["per_step_ms"] = {"min": min(per), "median": statistics.median(per), "max": max(per),
-                                        "note": "CUDA event after every step of the timed window (the step that contains the aggregation and its host read is the max)"}
+    def per_step(tag, ev0):
+        evs = [ev0] + step_ev[tag]
+        if len(evs) < 3:
+            return None
+        per = [round(a.elapsed_time(b), 3) for a, b in zip(evs[:-1], evs[1:])]
+        return {"min": min(per), "median": statistics.median(per), "max": max(per), "argmax_step": per.index(max(per)),
+                "note": "this rank's CUDA event after every step of the window; the step that contains the aggregation (waiting for "
+                        "the slowest rank included) and the host's read of its record is the max"}
+
+    out["config"]["per_step_ms"] = per_step("d", ev_d[0])
+    if smi:
+        smi.stop()
     if not args.no_e2e:
         ms_e = _max_over_ranks(ev_e[0].elapsed_time(ev_e[1]), dev)
         wall_e = _max_over_ranks((st["e"]["t1"] - st["e"]["t0"]) * 1e3, dev)
@@ -342,6 +371,7 @@ def run_ours(args) -> dict:
                       "note": "same engine, dataset moved to pinned host memory: native batch assembler, async H2D of each uint8 batch, "
                               "every step's loss copied D2H into pinned memory and read by the host one step later; "
                               "per-rank bytes (x N for the job)",
+                      "per_step_ms": per_step("e", ev_e[0]),
                       "clocks": st["e"].get("clocks"), "gpu_launches": st["e"].get("launches")}
     if not args.no_collective_table and hasattr(coll, "_launch") and "ResNet" in task.model_name:
         try:

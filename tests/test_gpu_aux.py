@@ -188,8 +188,9 @@ def _twin_grads(factory, inputs, loss_fn, tol, ref_double=False):
     lb.backward()
     FX.set_fast_path(True)
     assert float(la) == pytest.approx(float(lb), rel=tol)
-    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-        assert rel_err(pa.grad, pb.grad) < 10 * tol, n
+    errs = {n: rel_err(pa.grad, pb.grad) for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters())}
+    bad = {n: e for n, e in errs.items() if not e < 10 * tol}
+    assert not bad, "per-parameter gradient errors: %s" % errs
 
 
 def test_net_and_net2_fast_path_match_aten():
