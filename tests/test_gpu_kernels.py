@@ -304,11 +304,13 @@ def test_resnet18_fast_path_matches_aten_and_respects_freezing():
         lb = F.cross_entropy(b(x), y)
         lb.backward()
         FX.set_fast_path(True)
-        assert float(la) == pytest.approx(float(lb), rel=2e-2)
+        # error budget measured on a B200 (tools/measure_resnet_err.py, profiles/r2/r2_call5.log): whole-network gradients of
+        # the tf32 fast path vs an fp64 oracle 1.0e-3 ... 2.7e-3 (cuDNN with TF32 on: the same 1.0e-3 ... 2.8e-3), loss 5e-5
+        assert float(la) == pytest.approx(float(lb), rel=1e-3)
         for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
             assert (pa.grad is None) == (pb.grad is None), n
             if pb.grad is not None:
-                assert rel_err(pa.grad.contiguous(), pb.grad) < 6e-2, n
+                assert rel_err(pa.grad.contiguous(), pb.grad) < 1e-2, n
 
 
 # ------------------------------------------------------------------------------------------ losses
@@ -390,6 +392,8 @@ def test_engine_resnet_graphs_equal_eager_and_fast_close_to_aten():
     assert len(d_graph) == len(d_eager) == len(d_aten) == 16
     for a, b in zip(d_graph, d_eager):
         assert a == pytest.approx(b, rel=2e-2)
+    worst = max(abs(a - b) / abs(b) for a, b in zip(d_eager, d_aten))
+    print("fast-vs-ATen residual trace, worst relative deviation: %.3e" % worst)
     for a, b in zip(d_eager, d_aten):
         assert a == pytest.approx(b, rel=0.25)          # tf32 kernels vs fp32 ATen after a few Adam steps
     assert getattr(e1, "graph_replays", 0) > 0 and cuda_ops.launch_count() > 0

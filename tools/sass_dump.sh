@@ -11,7 +11,7 @@ declare -A KERNELS=(
   [igemm_persistent_128x3x2x1]='_ZN7fedb20023igemm_persistent_kernelILi128ELi3ELi2ELi1EEEv14CUtensorMap_stS1_S1_NS_11IgemmParamsE'
   [igemm_persistent_64x4x2x1]='_ZN7fedb20023igemm_persistent_kernelILi64ELi4ELi2ELi1EEEv14CUtensorMap_stS1_S1_NS_11IgemmParamsE'
   [conv3x3_ws_64]='_ZN7fedb20017conv3x3_ws_kernelILi64ELi30720ELi2EEEv14CUtensorMap_stS1_NS_10HaloParamsEii'
-  [wgrad_tf32]='_ZN7fedb20017wgrad_tf32_kernelE14CUtensorMap_stS0_NS_11WgradParamsE'
+  [wgrad_tf32]='_ZN7fedb20017wgrad_tf32_kernelE14CUtensorMap_stS0_S0_NS_11WgradParamsE'
   [block_reduce]='_ZN7fedb20019block_reduce_kernelENS_8CommArgsE'
   [bb_update]='_ZN7fedb20016bb_update_kernelENS_6BBArgsE'
   [lbfgs_two_loop]='_ZN7fedb20021lbfgs_two_loop_kernelEPKfS1_PKiiiiS1_fPfS4_'
