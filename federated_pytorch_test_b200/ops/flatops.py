@@ -34,6 +34,30 @@ def l1_l2(g: torch.Tensor) -> Tuple[float, float]:
     return float(g.abs().sum()), float(g.norm())
 
 
+def dir_stats(g: torch.Tensor, d: torch.Tensor) -> Tuple[float, float]:
+    """``(g.d, sum|d|)`` of a search direction — ONE device->host read on CUDA (the reference does ``float(dot)`` and
+    ``float(abs().sum())`` separately, lbfgsnew.py:679-681, :741; on CUDA the dot used to be a cuBLAS call)."""
+    if _cuda(g):
+        from . import cuda_ops
+
+        gtd = cuda_ops.ext().multi_dot([g.contiguous()], [d.contiguous()])
+        l1 = cuda_ops.ext().l1_l2(d)
+        a, b, _ = torch.cat([gtd, l1]).tolist()
+        return float(a), float(b)
+    return float(torch.dot(g, d)), float(d.abs().sum())
+
+
+def loss_and_l1(loss, g: torch.Tensor) -> Tuple[float, float]:
+    """``(float(loss), sum|g|)`` with one device->host read when ``loss`` is a CUDA tensor."""
+    if torch.is_tensor(loss) and loss.is_cuda and _cuda(g):
+        from . import cuda_ops
+
+        a, b, _ = torch.cat([loss.detach().reshape(1).float(), cuda_ops.ext().l1_l2(g)]).tolist()
+        return float(a), float(b)
+    lv = float(loss)
+    return lv, l1_l2(g)[0]
+
+
 def make_pair(g: torch.Tensor, g_prev: torch.Tensor, d: torch.Tensor, t: float, trust: float):
     """Curvature pair of one L-BFGS iteration.
 

@@ -468,7 +468,7 @@ class LBFGSNew(Optimizer):
             else:
                 t = lr
 
-            gtd = float(torch.dot(g, d))
+            gtd, d_l1 = flatops.dir_stats(g, d)      # one batched read; also feeds the step-size termination test below
             if math.isnan(gtd):
                 print("Warning grad norm infinite")
                 print("iter %d" % state["n_iter"])
@@ -491,9 +491,9 @@ class LBFGSNew(Optimizer):
 
             if inner != max_iter:
                 # re-evaluate (with gradient) unless this was the last inner iteration
-                loss = float(closure())
+                loss_t = closure()
                 g = v.grad()
-                g_l1, _ = flatops.l1_l2(g)
+                loss, g_l1 = flatops.loss_and_l1(loss_t, g)      # one batched read
                 if math.isnan(g_l1):
                     print("Warning: gradient nan")
                     break
@@ -505,7 +505,7 @@ class LBFGSNew(Optimizer):
                 break
             if g_l1 <= tol_g or gtd > -tol_x:
                 break
-            if float(d.abs().sum()) * abs(t) <= tol_x:
+            if d_l1 * abs(t) <= tol_x:
                 break
             if abs(loss - prev_loss) < tol_x:
                 break
