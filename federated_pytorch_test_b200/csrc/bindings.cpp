@@ -259,6 +259,21 @@ void conv_wgrad(Tensor x, Tensor dy, Tensor dw, int64_t stride, int64_t pad, int
                       cur_stream());
 }
 
+// Phase-packed stride-1 convolution (w: [4*Ci, kh, kw, Cin]) whose output lands pixel-shuffled: returns [N, 2*Ho, 2*Wo, Ci].
+bool conv_shuffle_supported(int64_t Ho, int64_t Wo, int64_t Cin, int64_t Ci) {
+  return fb::conv_shuffle_supported((int)Ho, (int)Wo, (int)Cin, (int)Ci);
+}
+Tensor conv2d_nhwc_shuffle(Tensor x, Tensor w, int64_t pad, int64_t Ho, int64_t Wo) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.size(3) == w.size(3) && w.size(0) % 4 == 0, "conv2d_nhwc_shuffle: x [N,H,W,Cin], w [4*Ci,kh,kw,Cin]");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), Cin = (int)x.size(3);
+  const int C4 = (int)w.size(0), kh = (int)w.size(1), kw = (int)w.size(2);
+  auto out = torch::empty({NB, 2 * Ho, 2 * Wo, C4 / 4}, x.options());
+  fb::conv2d_nhwc_shuffle_tf32(fptr(x), fptr(w), fptr_mut(out), NB, H, W, Cin, C4, kh, kw, (int)pad, (int)Ho, (int)Wo, cur_stream());
+  return out;
+}
+
 // y += conv(x, w), in place (experimental)
 Tensor conv2d_nhwc_accumulate(Tensor x, Tensor w, Tensor y, int64_t stride, int64_t pad, int64_t dil) {
   CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_F32_CUDA(y); CHECK_CONTIG(x); CHECK_CONTIG(w); CHECK_CONTIG(y);
@@ -606,6 +621,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv2d_nhwc_sized", &conv2d_nhwc_sized);
   m.def("conv2d_nhwc_bias_act", &conv2d_nhwc_bias_act);
   m.def("conv2d_nhwc_accumulate", &conv2d_nhwc_accumulate);
+  m.def("conv2d_nhwc_shuffle", &conv2d_nhwc_shuffle);
+  m.def("conv_shuffle_supported", &conv_shuffle_supported);
   m.def("conv_wgrad", &conv_wgrad);
   m.def("conv_wgrad_supported", &conv_wgrad_supported);
   m.def("cross_entropy_fwd", &cross_entropy_fwd);

@@ -55,6 +55,10 @@ void conv2d_nhwc_bias_act_tf32(const float* x, const float* w, const float* bias
                                int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
                                cudaStream_t stream);
 
+// phase-packed stride-1 conv stored straight into the pixel-shuffled [N, 2Ho, 2Wo, C4/4] result (stride-2 dgrad, transposed conv)
+bool conv_shuffle_supported(int H_out, int W_out, int C_in, int Ci_out);
+void conv2d_nhwc_shuffle_tf32(const float* x, const float* w, float* out, int NB, int H, int W, int C_in, int C4, int kh, int kw,
+                              int pad, int H_out, int W_out, cudaStream_t stream);
 // weight gradient on tcgen05 (MN-major operands, split over the pixel range, red.add into dw)
 bool conv_wgrad_supported(int C_x, int C_out, int stride, int W_out, int H_out);
 void conv_wgrad_tf32(const float* x, const float* dy, float* dw, int NB, int H, int W, int C_x, int C_w, int C_out, int kh,

@@ -132,6 +132,8 @@ static int env_int(const char* name, int dflt) {
 static long long* g_conv_trace = nullptr;
 void set_conv_trace(long long* buf) { g_conv_trace = buf; }
 
+static const CUtensorMap* g_out_map_override = nullptr;     // set (and cleared) by conv2d_nhwc_shuffle_tf32 around its dispatch
+
 template <int BN, int ST, int KPS, int MT>
 static void launch_p(const CUtensorMap& ta, const CUtensorMap& tb, IgemmParams p, cudaStream_t stream) {
   using S = IgemmPSmem<BN, ST, KPS, MT>;
@@ -153,7 +155,8 @@ static void launch_p(const CUtensorMap& ta, const CUtensorMap& tb, IgemmParams p
   p.trace = g_conv_trace;
   // output map: box = 32 columns x 32 rows (one epilogue chunk of one warp), 128B swizzle like the operand maps
   p.tma_store = ((p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && env_int("FEDB200_TMA_STORE", 1) != 0) ? 1 : 0;
-  const CUtensorMap tc = p.tma_store ? make_tmap_out(p.out, p.M, p.N, p.ldo, 32) : ta;
+  if (g_out_map_override != nullptr) p.tma_store = 1;
+  const CUtensorMap tc = g_out_map_override != nullptr ? *g_out_map_override : (p.tma_store ? make_tmap_out(p.out, p.M, p.N, p.ldo, 32) : ta);
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(IG_THREADS), S::TOTAL, stream, ta, tb, tc, p);
   if (e != cudaSuccess) throw std::runtime_error(std::string("fedb200: persistent igemm launch: ") + cudaGetErrorString(e));
@@ -539,6 +542,77 @@ static void conv2d_generic(const float* x, const float* w, float* y, float* stat
   }
   if (pair) dispatch2(bn, ta, tb, p, stream); else dispatch(bn, cl, ta, tb, p, stream);
   if (p.k_splits > 1 && stats != nullptr) col_stats(y, stats, M, C_out, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stride-2 data gradient / transposed convolution WITHOUT the pixel-shuffle pass: the phase-packed stride-1 convolution
+// (ops/conv_math.py: output channels (ph, pw, ci)) stores every 32 x 32 epilogue chunk straight to
+// out[n, 2 ho + ph, 2 wo + pw, ci0 ..] through a 5-D tensor map {ci, pw, wo, ph, n * Ho + ho} over the [N, 2Ho, 2Wo, Ci] result.
+// Round 1 wrote [N, Ho, Wo, 4 Ci] and copied it (6 copies, 230 MB of traffic per training step, profiles/r2_step_kernels.md).
+// ------------------------------------------------------------------------------------------------
+bool conv_shuffle_supported(int H_out, int W_out, int C_in, int Ci_out) {
+  if (env_int("FEDB200_SHUFFLE_STORE", 1) == 0) return false;
+  if (!conv_geometry_supported(H_out, W_out, C_in, 1)) return false;
+  if (Ci_out % 32 != 0) return false;                         // a 32-column chunk must stay inside one phase
+  if (W_out > 32 || (32 % W_out) != 0) return false;          // a 32-row chunk = whole output rows
+  if (env_int("FEDB200_KPS", 2) == 1 || env_int("FEDB200_PERSIST", 1) == 0 || env_int("FEDB200_CLUSTER", 1) != 1 ||
+      env_int("FEDB200_2CTA", 0) != 0)
+    return false;                                             // persistent kernel only
+  return true;
+}
+
+void conv2d_nhwc_shuffle_tf32(const float* x, const float* w, float* out, int NB, int H, int W, int C_in, int C4, int kh, int kw,
+                              int pad, int H_out, int W_out, cudaStream_t stream) {
+  const int Ci = C4 / 4;
+  if (!conv_shuffle_supported(H_out, W_out, C_in, Ci)) throw std::runtime_error("fedb200: shuffled conv store not supported for this shape");
+  const int rows = 128 / W_out;
+  const int boxH = rows <= H_out ? rows : H_out;
+  const int boxN = rows <= H_out ? 1 : rows / H_out;
+  const int M = NB * H_out * W_out;
+  const int bn = pick_block_n(M, C4);
+  CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, 1);
+  CUtensorMap tb = make_tmap_2d(w, C4, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn);
+  CUtensorMap tc;
+  {
+    cuuint64_t dims[5] = {cuuint64_t(Ci), 2, cuuint64_t(W_out), 2, cuuint64_t(NB) * H_out};
+    cuuint64_t strides[4] = {cuuint64_t(Ci) * 4, cuuint64_t(2) * Ci * 4, cuuint64_t(2) * W_out * Ci * 4, cuuint64_t(4) * W_out * Ci * 4};
+    cuuint32_t box[5] = {32, 1, cuuint32_t(W_out), 1, cuuint32_t(32 / W_out)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    check_cu(encode_fn()(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
+             "cuTensorMapEncodeTiled(shuffle)");
+  }
+  IgemmParams p{};
+  p.M = M; p.N = C4;
+  p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
+  p.num_k_blocks = kh * kw * p.cblocks;
+  p.taps_w = kw; p.b_cols_per_tap = C_in; p.is_conv = 1;
+  p.HW_out = H_out * W_out; p.W_out = W_out;
+  p.stride = 1; p.pad = pad; p.dil = 1;
+  p.out = out; p.ldo = C4; p.bias = nullptr; p.act = 0; p.stats = nullptr;
+  p.k_splits = 1; p.kb_per_split = p.num_k_blocks; p.dbg = env_int("FEDB200_DBG", 0);
+  p.shuffle_ci = Ci;
+  {   // split-K exactly as conv2d_generic: partial tiles are reduce-added (5-D) into the zeroed result
+    const int ctas = ((M + IG_BLOCK_M - 1) / IG_BLOCK_M) * ((C4 + bn - 1) / bn);
+    int splits = env_int("FEDB200_SPLITK", 0);
+    if (splits <= 0) {
+      splits = 1;
+      while (splits < 8 && ctas * splits * 2 <= 160 && p.num_k_blocks / (splits * 2) >= 6) splits *= 2;
+    }
+    if (splits > 1) {
+      p.kb_per_split = (p.num_k_blocks + splits - 1) / splits;
+      p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+      cudaMemsetAsync(out, 0, size_t(M) * C4 * sizeof(float), stream);
+    }
+  }
+  g_out_map_override = &tc;
+  try {
+    dispatch_p(bn, ta, tb, p, stream);
+  } catch (...) {
+    g_out_map_override = nullptr;
+    throw;
+  }
+  g_out_map_override = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -268,8 +268,18 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             if (p.tma_store) fence_proxy_async();
             __syncwarp();
             if (p.tma_store && lane == 0 && !(p.dbg & 4)) {
-              if (p.k_splits > 1 || p.accumulate) tma_reduce_add_2d(&tmap_c, stage, c.n0 + c0, row0);
-              else tma_store_2d(&tmap_c, stage, c.n0 + c0, row0);
+              if (p.shuffle_ci > 0) {
+                const int pc = c.n0 + c0;                       // packed channel (ph, pw, ci) of this chunk
+                const int phase = pc / p.shuffle_ci;
+                if (pc < p.N) {
+                  if (p.k_splits > 1) tma_reduce_add_5d(&tmap_c, stage, pc - phase * p.shuffle_ci, phase & 1, 0, phase >> 1, row0 / p.W_out);
+                  else tma_store_5d(&tmap_c, stage, pc - phase * p.shuffle_ci, phase & 1, 0, phase >> 1, row0 / p.W_out);
+                }
+              } else if (p.k_splits > 1 || p.accumulate) {
+                tma_reduce_add_2d(&tmap_c, stage, c.n0 + c0, row0);
+              } else {
+                tma_store_2d(&tmap_c, stage, c.n0 + c0, row0);
+              }
               tma_store_commit();
             }
           }

@@ -49,6 +49,9 @@ struct IgemmParams {
   int accumulate;        // persistent kernel: out += result (bulk reduce-add / atomics) instead of out = result; no memset
   int tma_store;         // persistent kernel: write the output with bulk tensor stores / reduce-adds (needs ldo % 4 == 0)
   long long* trace;      // optional [16] clock64 stamps of CTA 0 (tools/trace_conv.py); nullptr in production
+  int shuffle_ci;        // persistent kernel, > 0: the N columns are (ph, pw, ci) phase-packed channels of a stride-2 data gradient /
+                         // transposed conv; each 32 x 32 chunk is stored to out[n, 2 ho + ph, 2 wo + pw, ci0 .. ci0 + 31] through a
+                         // 5-D tensor map (no separate pixel-shuffle pass).  shuffle_ci = channels of the shuffled output.
 };
 
 // KPS = k-blocks (of 32 fp32 = one 128-B swizzle row) per pipeline stage.  One producer/consumer barrier round trip

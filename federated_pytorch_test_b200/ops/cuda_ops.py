@@ -265,10 +265,17 @@ def _s2_dgrad_supported(e, xn: torch.Tensor, dy: torch.Tensor, kh: int, kw: int,
 def _s2_dgrad(e, dy: torch.Tensor, wk: torch.Tensor, trainable: bool, persistent: bool = True) -> torch.Tensor:
     """dx [N, 2Ho, 2Wo, Ci] of a stride-2 convolution: one stride-1 implicit GEMM over dy + a pixel shuffle."""
     wp = _packed_s2_weight(wk, trainable, persistent)
+    Ho, Wo, Co = dy.shape[1], dy.shape[2], dy.shape[3]
+    Ci = wp.shape[0] // 4
+    # the kernel stores every epilogue chunk straight to dx[n, 2 ho + ph, 2 wo + pw, :] (5-D tensor map): no pixel-shuffle copy
+    shuffle = bool(e.conv_shuffle_supported(Ho, Wo, Co, Ci))
     if wk.shape[1] == 1:      # 1x1: only tap (0, 0) of the 2x2 window is populated -> run it as a 1x1 convolution
         w1 = wp[:, 0:1, 0:1, :].contiguous()
+        if shuffle:
+            return e.conv2d_nhwc_shuffle(dy, w1, 0, Ho, Wo)
         return conv_math.dgrad_s2(dy, w1, lambda x, w: e.conv2d_nhwc(x, w, None, 1, 0, 1))
-    Ho, Wo = dy.shape[1], dy.shape[2]
+    if shuffle:
+        return e.conv2d_nhwc_shuffle(dy, wp, 0, Ho, Wo)
     return conv_math.dgrad_s2(dy, wp, lambda x, w: e.conv2d_nhwc_sized(x, w, None, 1, 0, 1, Ho, Wo))
 
 
