@@ -33,7 +33,7 @@ def run_aux_bench(args) -> dict:
         first = straddle_window(K, W, 1, per_round)
         rounds = -(-(first + K) // per_round) + 1
         cfg = mod.Config(K=N, Nloop=1000, Nadmm=rounds, Niter=per_round, load_model=False, init_model=True, save_model=False,
-                         be_verbose=False, check_results=False, graphs=False, fast=not args.no_fast, collective=args.collective, seed=69)
+                         be_verbose=False, check_results=False, graphs=not args.no_graphs, fast=not args.no_fast, collective=args.collective, seed=69)
     else:
         per_round, batch = 49, 128                       # the K = 8 shard: 49 minibatches per round
         mod = federated_vae if args.driver == "vae" else federated_vae_cl

@@ -145,6 +145,7 @@ class EngineConfig:
     be_verbose: bool = False
     diagnostics: str = "post"        # 'post' = reference (extra forward after the step, Q17) | 'pre' = reuse closure loss
     graphs: bool = False             # CUDA-graph the Adam minibatch step
+    graph_closures: bool = True      # ... and (with graphs=True) the L-BFGS closure: one graph for gradient evaluations, one for probes
     max_minibatches: Optional[int] = None   # cap per round (benchmarks / smoke tests)
     aggregate_in_epoch_loop: bool = True    # reference: aggregation sits inside the epoch loop
     reset_optimizer_each_epoch: bool = False  # no_consensus_multi.py:129-132 recreates Adam every epoch (Q18)
@@ -225,6 +226,13 @@ class Engine:
                 return loss
 
             opt.step(closure)
+        elif cfg.graphs and cfg.graph_closures and rep.device.type == "cuda" and isinstance(opt, LBFGSNew):
+            gc_ = self._graphed_closure(rep, opt, visit, batch)
+            gc_.bind(batch, pen)
+            opt.step(gc_)
+            if cfg.diagnostics == "post":
+                return gc_.evaluate(False)[1]
+            return gc_.first
         else:
             x = rep.block(visit)
             g = rep.block_grad(visit)
@@ -471,6 +479,19 @@ class Engine:
     # ------------------------------------------------------------------
     # CUDA-graphed Adam step
     # ------------------------------------------------------------------
+    def _graphed_closure(self, rep: Replica, opt, visit: Visit, batch):
+        """One graphed closure per replica: the graphs of the previous block visit are dropped (their activations pools are
+        as large as the network's; an L-BFGS visit re-creates its optimizer anyway, Q18)."""
+        from .graphs import GraphedClosure
+
+        slot = ("lbfgs", rep.ck)
+        ident = (visit.model, visit.lo, visit.hi, tuple(tuple(t.shape) for t in batch if torch.is_tensor(t)))
+        cur = self._graphs.get(slot)
+        if cur is None or cur[0] != ident or cur[1].opt is not opt:
+            cur = (ident, GraphedClosure(self, rep, opt, visit, batch))
+            self._graphs[slot] = cur
+        return cur[1]
+
     def _graphed_step(self, rep: Replica, opt: BlockAdam, visit: Visit, batch, pen: Penalty) -> torch.Tensor:
         from .graphs import GraphedAdamStep
 

@@ -39,8 +39,9 @@ def _grad_sink():
     return contextlib.nullcontext()
 
 
-def capture_graph(stream, body):
-    """Capture ``body()`` into a new CUDA graph on ``stream``; returns ``(graph, body's return value)``.
+def capture_graph(stream, body, pool=None):
+    """Capture ``body()`` into a new CUDA graph on ``stream``; returns ``(graph, body's return value)``.  ``pool``: the
+    memory pool of another graph that never runs concurrently with this one (its private memory is shared).
 
     A CUDAGraph that is garbage (e.g. the graphs of a previous Engine, kept alive by a reference cycle) must not be
     finalised while a capture is in progress: cudaGraphExecDestroy is "not permitted when stream is capturing" and
@@ -54,7 +55,7 @@ def capture_graph(stream, body):
     was_enabled = gc.isenabled()
     gc.disable()
     try:
-        with torch.cuda.graph(g, stream=stream):
+        with torch.cuda.graph(g, stream=stream, pool=pool):
             out = body()
     finally:
         if was_enabled:
@@ -155,3 +156,98 @@ class GraphedAdamStep:
         self.engine.graph_replays += 1
         self.engine.graph_kernel_launches += self.kernels_per_replay
         return self.loss_out.clone()
+
+
+class GraphedClosure:
+    """The L-BFGS closure as two CUDA graphs per (replica, block visit, batch shape).
+
+    ``LBFGSNew.step`` evaluates its closure 5-20 times per minibatch (/root/reference/src/lbfgsnew.py:590-659: gradient
+    evaluations with autograd on, line-search probes under ``no_grad``); for the small VAE-CL / CPC networks every one of
+    those evaluations is ~100-300 launches of microsecond kernels, i.e. host-bound.  Captured here:
+
+    * ``grad``: zero the block gradient, forward, loss, backward (weight-gradient kernels accumulate straight into the arena's
+      gradient slice), closed-form FedProx / ADMM / elastic-net gradient, total loss;
+    * ``eval``: no-grad forward + penalty value.
+
+    Both read the minibatch from static buffers and the parameters from the arena (the line search moves ``x`` in place), and
+    write ``[total, data-loss]`` into a static pair; the two graphs share one memory pool.  Nothing inside touches the host."""
+
+    WARMUP = 2
+
+    def __init__(self, engine, rep, opt, visit, batch):
+        self.engine, self.rep, self.opt, self.visit = engine, rep, opt, visit
+        self.static = [t.clone() if torch.is_tensor(t) else t for t in batch]
+        self.stream = torch.cuda.Stream(device=rep.device)
+        self.graph = {True: None, False: None}
+        self.out = {True: None, False: None}
+        self.kernels = {True: 0, False: 0}
+        self.calls = {True: 0, False: 0}
+        self.pen = None
+        self.pen_key = None
+        self.first = None
+
+    def _key(self, pen):
+        rho_key = ("dev", pen.rho_dev.data_ptr()) if pen.rho_dev is not None else ("host", float(pen.rho))
+        return (pen.z.data_ptr() if pen.z is not None else 0, pen.y.data_ptr() if pen.y is not None else 0, rho_key)
+
+    def bind(self, batch, pen) -> None:
+        """Start of one ``opt.step``: new minibatch into the static buffers; a changed consensus buffer invalidates the graphs."""
+        key = self._key(pen)
+        if key != self.pen_key:
+            self.pen_key = key
+            self.graph = {True: None, False: None}
+            self.calls = {True: 0, False: 0}
+        self.pen = pen
+        for dst, src in zip(self.static, batch):
+            if torch.is_tensor(dst):
+                if dst.shape != src.shape:
+                    raise RuntimeError("graphed closure called with a different batch shape")
+                dst.copy_(src, non_blocking=True)
+        self.first = None
+
+    def _body(self, with_grad: bool) -> torch.Tensor:
+        from ..ops import flatops
+
+        task, rep, visit, pen = self.engine.task, self.rep, self.visit, self.pen
+        x = rep.block(visit)
+        has_pen = pen.z is not None or visit.lambda1 != 0.0 or visit.lambda2 != 0.0
+        if with_grad:
+            self.opt.zero_grad()
+            loss = task.loss(rep, self.static)
+            with _grad_sink():
+                loss.backward()
+            if has_pen:
+                flatops.add_penalty_grad_(rep.block_grad(visit), x, pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2)
+        else:
+            with torch.no_grad():
+                loss = task.loss(rep, self.static)
+        base = loss.detach()
+        total = base + flatops.penalty_value(x, pen.z, pen.y, pen.rho, visit.lambda1, visit.lambda2) if has_pen else base
+        return torch.stack([total.reshape(()), base.reshape(())])
+
+    def evaluate(self, with_grad: bool) -> torch.Tensor:
+        """``[total, data loss]`` (device) at the current parameters."""
+        self.calls[with_grad] += 1
+        if self.graph[with_grad] is None:
+            if self.calls[with_grad] <= self.WARMUP:
+                with torch.enable_grad() if with_grad else torch.no_grad():
+                    out = self._body(with_grad)
+                if self.first is None:
+                    self.first = out[1]
+                return out
+            other = self.graph[not with_grad]
+            before = cuda_ops.launch_count()
+            with torch.enable_grad() if with_grad else torch.no_grad():
+                self.graph[with_grad], self.out[with_grad] = capture_graph(
+                    self.stream, lambda: self._body(with_grad), pool=other.pool() if other is not None else None)
+            self.kernels[with_grad] = cuda_ops.launch_count() - before
+        self.graph[with_grad].replay()
+        self.engine.graph_replays += 1
+        self.engine.graph_kernel_launches += self.kernels[with_grad]
+        out = self.out[with_grad].clone()
+        if self.first is None:
+            self.first = out[1]
+        return out
+
+    def __call__(self) -> torch.Tensor:
+        return self.evaluate(torch.is_grad_enabled())[0]

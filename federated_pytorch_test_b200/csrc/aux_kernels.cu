@@ -46,58 +46,97 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // C[i, j] (+)= act( sum_k A(i, k) * B(k, j) + bias[j] ),  A(i,k) = a[i*sa_i + k*sa_k],  B(k,j) = b[k*sb_k + j*sb_j]
-// 64 x 64 tile per CTA, 16-deep k tiles, 256 threads x (4 x 4) outputs.  True fp32 (FFMA).
+// BM x BN tile per CTA (64 x 64, or 32 x 32 when the 64-tiles would leave most SMs idle: the dense layers of the model zoo
+// are 128 x 16 ... 1280 x 128 outputs), 16-deep k tiles, 256 threads x (BM/16 x BN/16) outputs, true fp32 (FFMA).
+// The next k tile is fetched into registers while the current one is multiplied (one barrier per tile): these GEMMs are
+// latency bound — the first version (load, barrier, multiply, barrier) took 11-17 us for 1.5-75 MFLOP (r2_call14.log).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int GF_BM = 64, GF_BN = 64, GF_BK = 16;
+constexpr int GF_BK = 16;
 
+template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ bias, float* __restrict__ c,
                 int M, int N, int K, long long sa_i, long long sa_k, long long sb_k, long long sb_j, int ldc, int act, int accumulate) {
-  __shared__ float As[GF_BK][GF_BM + 4];
-  __shared__ float Bs[GF_BK][GF_BN + 4];
+  constexpr int TM = BM / 16, TN = BN / 16;            // outputs per thread
+  constexpr int EA = BM * GF_BK / 256, EB = BN * GF_BK / 256;
+  __shared__ float As[2][GF_BK][BM + 4];
+  __shared__ float Bs[2][GF_BK][BN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int i0 = blockIdx.y * GF_BM, j0 = blockIdx.x * GF_BN;
-  float acc[4][4];
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  float acc[TM][TN];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < TM; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += GF_BK) {
+    for (int v = 0; v < TN; ++v) acc[u][v] = 0.f;
+  float ra[EA], rb[EB];
+  // element e of this thread inside a tile: the contiguous dimension runs along consecutive threads
+  auto a_pos = [&](int e, int& ai, int& ak) {
+    const int idx = threadIdx.x + e * 256;
+    if (sa_k == 1) { ak = idx % GF_BK; ai = idx / GF_BK; } else { ai = idx % BM; ak = idx / BM; }
+  };
+  auto b_pos = [&](int e, int& bj, int& bk) {
+    const int idx = threadIdx.x + e * 256;
+    if (sb_j == 1) { bj = idx % BN; bk = idx / BN; } else { bk = idx % GF_BK; bj = idx / GF_BK; }
+  };
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = threadIdx.x + e * 256;           // 1024 elements per tile
-      // A tile: prefer the contiguous dimension along consecutive threads
+    for (int e = 0; e < EA; ++e) {
       int ai, ak;
-      if (sa_k == 1) { ak = idx & 15; ai = idx >> 4; } else { ai = idx & 63; ak = idx >> 6; }
+      a_pos(e, ai, ak);
       const int gi = i0 + ai, gk = k0 + ak;
-      As[ak][ai] = (gi < M && gk < K) ? __ldg(a + gi * sa_i + gk * sa_k) : 0.f;
-      int bk, bj;
-      if (sb_j == 1) { bj = idx & 63; bk = idx >> 6; } else { bk = idx & 15; bj = idx >> 4; }
-      const int gj = j0 + bj, gk2 = k0 + bk;
-      Bs[bk][bj] = (gj < N && gk2 < K) ? __ldg(b + gk2 * sb_k + gj * sb_j) : 0.f;
+      ra[e] = (gi < M && gk < K) ? __ldg(a + gi * sa_i + gk * sa_k) : 0.f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      int bj, bk;
+      b_pos(e, bj, bk);
+      const int gj = j0 + bj, gk = k0 + bk;
+      rb[e] = (gj < N && gk < K) ? __ldg(b + gk * sb_k + gj * sb_j) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < EA; ++e) {
+      int ai, ak;
+      a_pos(e, ai, ak);
+      As[buf][ak][ai] = ra[e];
+    }
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      int bj, bk;
+      b_pos(e, bj, bk);
+      Bs[buf][bk][bj] = rb[e];
+    }
+  };
+  const int nk = (K + GF_BK - 1) / GF_BK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * GF_BK);          // in flight while this tile is multiplied
 #pragma unroll
     for (int kk = 0; kk < GF_BK; ++kk) {
-      float av[4], bv[4];
+      float av[TM], bv[TN];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) av[u] = As[kk][ty * 4 + u];
+      for (int u = 0; u < TM; ++u) av[u] = As[cur][kk][ty * TM + u];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) bv[v] = Bs[kk][tx * 4 + v];
+      for (int v = 0; v < TN; ++v) bv[v] = Bs[cur][kk][tx * TN + v];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < TM; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+        for (int v = 0; v < TN; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
     }
+    if (kt + 1 < nk) stash(cur ^ 1);                   // the other buffer was last read before the previous barrier
     __syncthreads();
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int gi = i0 + ty * 4 + u;
+  for (int u = 0; u < TM; ++u) {
+    const int gi = i0 + ty * TM + u;
     if (gi >= M) continue;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int gj = j0 + tx * 4 + v;
+    for (int v = 0; v < TN; ++v) {
+      const int gj = j0 + tx * TN + v;
       if (gj >= N) continue;
       float r = acc[u][v];
       if (bias != nullptr) r += __ldg(bias + gj);
@@ -110,8 +149,14 @@ gemm_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, const 
 
 void gemm_f32(const float* a, const float* b, const float* bias, float* c, int M, int N, int K, long long sa_i, long long sa_k,
               long long sb_k, long long sb_j, int ldc, int act, int accumulate, cudaStream_t s) {
-  dim3 grid((N + GF_BN - 1) / GF_BN, (M + GF_BM - 1) / GF_BM);
-  gemm_f32_kernel<<<grid, 256, 0, s>>>(a, b, bias, c, M, N, K, sa_i, sa_k, sb_k, sb_j, ldc, act, accumulate);
+  const int ctas64 = ((N + 63) / 64) * ((M + 63) / 64);
+  if (ctas64 < aux_sms() / 2) {
+    dim3 grid((N + 31) / 32, (M + 31) / 32);
+    gemm_f32_kernel<32, 32><<<grid, 256, 0, s>>>(a, b, bias, c, M, N, K, sa_i, sa_k, sb_k, sb_j, ldc, act, accumulate);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_f32_kernel<64, 64><<<grid, 256, 0, s>>>(a, b, bias, c, M, N, K, sa_i, sa_k, sb_k, sb_j, ldc, act, accumulate);
+  }
   aux_check("gemm_f32");
 }
 

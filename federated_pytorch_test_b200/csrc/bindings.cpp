@@ -274,6 +274,28 @@ Tensor conv2d_nhwc_shuffle(Tensor x, Tensor w, int64_t pad, int64_t Ho, int64_t 
   return out;
 }
 
+// `B` dilated convolutions of the same input in one launch: w [Co_total, B * kh, kw, Ci] block diagonal, y [N, Ho, Wo, Co_total]
+bool conv_multidil_supported(int64_t Ho, int64_t Wo, int64_t Ci, int64_t stride, int64_t branches) {
+  return fb::conv_multidil_supported((int)Ho, (int)Wo, (int)Ci, (int)stride, (int)branches);
+}
+Tensor conv2d_nhwc_multidil(Tensor x, Tensor w, c10::optional<Tensor> bias, bool act, int64_t kh, int64_t stride,
+                            std::vector<int64_t> dils, std::vector<int64_t> pads, int64_t Ho, int64_t Wo) {
+  CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
+  TORCH_CHECK(x.dim() == 4 && w.dim() == 4 && x.size(3) == w.size(3), "conv2d_nhwc_multidil: x [N,H,W,Ci], w [Co,B*kh,kw,Ci]");
+  const int B = (int)dils.size();
+  TORCH_CHECK(B >= 1 && B <= 8 && (int)pads.size() == B && w.size(1) == B * kh, "conv2d_nhwc_multidil: branch tables");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int NB = (int)x.size(0), H = (int)x.size(1), W = (int)x.size(2), Ci = (int)x.size(3);
+  const int Co = (int)w.size(0), kw = (int)w.size(2);
+  if (bias.has_value() && bias->defined()) TORCH_CHECK(bias->numel() == Co && bias->is_contiguous(), "bias must be [Co]");
+  int d[8], pd[8];
+  for (int b = 0; b < B; ++b) { d[b] = (int)dils[b]; pd[b] = (int)pads[b]; }
+  auto y = torch::empty({NB, Ho, Wo, Co}, x.options());
+  fb::conv2d_nhwc_multidil_tf32(fptr(x), fptr(w), opt_ptr(bias), act ? 1 : 0, fptr_mut(y), NB, H, W, Ci, Co, B, (int)kh, kw,
+                                (int)stride, d, pd, (int)Ho, (int)Wo, cur_stream());
+  return y;
+}
+
 // y += conv(x, w), in place (experimental)
 Tensor conv2d_nhwc_accumulate(Tensor x, Tensor w, Tensor y, int64_t stride, int64_t pad, int64_t dil) {
   CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_F32_CUDA(y); CHECK_CONTIG(x); CHECK_CONTIG(w); CHECK_CONTIG(y);
@@ -623,6 +645,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv2d_nhwc_accumulate", &conv2d_nhwc_accumulate);
   m.def("conv2d_nhwc_shuffle", &conv2d_nhwc_shuffle);
   m.def("conv_shuffle_supported", &conv_shuffle_supported);
+  m.def("conv2d_nhwc_multidil", &conv2d_nhwc_multidil);
+  m.def("conv_multidil_supported", &conv_multidil_supported);
   m.def("conv_wgrad", &conv_wgrad);
   m.def("conv_wgrad_supported", &conv_wgrad_supported);
   m.def("cross_entropy_fwd", &cross_entropy_fwd);

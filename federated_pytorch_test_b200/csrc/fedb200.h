@@ -59,6 +59,11 @@ void conv2d_nhwc_bias_act_tf32(const float* x, const float* w, const float* bias
 bool conv_shuffle_supported(int H_out, int W_out, int C_in, int Ci_out);
 void conv2d_nhwc_shuffle_tf32(const float* x, const float* w, float* out, int NB, int H, int W, int C_in, int C4, int kh, int kw,
                               int pad, int H_out, int W_out, cudaStream_t stream);
+// `branches` dilated convolutions of one input as one launch writing the concatenated output (CPC encoder stem)
+bool conv_multidil_supported(int H_out, int W_out, int C_in, int stride, int branches);
+void conv2d_nhwc_multidil_tf32(const float* x, const float* w, const float* bias, int act, float* y, int NB, int H, int W, int C_in,
+                               int C_out, int branches, int kh, int kw, int stride, const int* dils, const int* pads, int H_out,
+                               int W_out, cudaStream_t stream);
 // weight gradient on tcgen05 (MN-major operands, split over the pixel range, red.add into dw)
 bool conv_wgrad_supported(int C_x, int C_out, int stride, int W_out, int H_out);
 void conv_wgrad_tf32(const float* x, const float* dy, float* dw, int NB, int H, int W, int C_x, int C_w, int C_out, int kh,

@@ -51,14 +51,18 @@ static void check_cu(CUresult r, const char* what) {
 
 // fp32 matrix [rows, cols] with row pitch ld (elements): box = [box_rows x 32 cols], 128B swizzle,
 // loaded as TF32 (round-to-nearest on the way into shared memory), out-of-bounds zero-filled.
-static CUtensorMap make_tmap_2d(const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// cw = channels (K elements) per operand row: 32 (one tap per k-block) or 16 / 8 (tap packing, IgemmParams::cw)
+static CUtensorMapSwizzle swizzle_for(int cw) {
+  return cw == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : (cw == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static CUtensorMap make_tmap_2d(const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, int cw = IG_BLOCK_K) {
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {uint32_t(IG_BLOCK_K), box_rows};
+  cuuint32_t box[2] = {uint32_t(cw), box_rows};
   cuuint32_t estr[2] = {1, 1};
   check_cu(encode_fn()(&m, tmap_dtype(),2, const_cast<float*>(ptr), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
            "cuTensorMapEncodeTiled(2d)");
   return m;
@@ -80,14 +84,14 @@ static CUtensorMap make_tmap_out(float* ptr, uint64_t rows, uint64_t cols, uint6
 // NHWC activation viewed as [C, W, H, N]; a box covers boxN x boxH x boxW output pixels (traversal stride = conv
 // stride) x 32 channels and lands in shared memory as a [128 pixels x 128 B] K-major swizzled tile.
 static CUtensorMap make_tmap_nhwc(const float* ptr, uint64_t N, uint64_t H, uint64_t W, uint64_t C, uint32_t boxN,
-                                  uint32_t boxH, uint32_t boxW, uint32_t stride) {
+                                  uint32_t boxH, uint32_t boxW, uint32_t stride, int cw = IG_BLOCK_K) {
   CUtensorMap m;
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {C * sizeof(float), W * C * sizeof(float), H * W * C * sizeof(float)};
-  cuuint32_t box[4] = {uint32_t(IG_BLOCK_K), boxW * stride, boxH * stride, boxN};
+  cuuint32_t box[4] = {uint32_t(cw), boxW * stride, boxH * stride, boxN};
   cuuint32_t estr[4] = {1, stride, stride, 1};
   check_cu(encode_fn()(&m, tmap_dtype(),4, const_cast<float*>(ptr), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cw), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE),
            "cuTensorMapEncodeTiled(nhwc)");
   return m;
@@ -493,6 +497,16 @@ void conv2d_nhwc_accumulate_tf32(const float* x, const float* w, float* y, int N
   conv2d_generic(x, w, y, nullptr, nullptr, 0, NB, H, W, C_in, C_out, kh, kw, stride, pad, dil, H_out, W_out, stream, 1);
 }
 
+// Tap packing (IgemmParams::cw): with C_in <= 16 a 32-wide k-block holds 4 (C_in <= 8) or 2 taps instead of one tap padded with
+// zeros.  Only the persistent kernel implements it.  FEDB200_TAP_PACK=0 switches it off (A/B runs).
+static int pick_tap_pack(int C_in, bool persistent_eligible) {
+  if (!persistent_eligible || env_int("FEDB200_TAP_PACK", 1) == 0 || C_in > 16 || (C_in & 3)) return IG_BLOCK_K;
+  return C_in <= 8 ? 8 : 16;
+}
+static bool persistent_default() {
+  return env_int("FEDB200_KPS", 2) != 1 && env_int("FEDB200_PERSIST", 1) != 0;
+}
+
 static void conv2d_generic(const float* x, const float* w, float* y, float* stats, const float* bias, int act, int NB, int H,
                            int W, int C_in, int C_out, int kh, int kw, int stride, int pad, int dil, int H_out, int W_out,
                            cudaStream_t stream, int accumulate) {
@@ -507,12 +521,18 @@ static void conv2d_generic(const float* x, const float* w, float* y, float* stat
   const int cl = pair ? 2 : pick_cluster(M);
   // one TMA box per operand and k-block: splitting a tile into several smaller boxes was measured SLOWER
   // (profiles/r1_run10_tma_subbox.log)
-  CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride);
-  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn / cl);
+  const int cw = pick_tap_pack(C_in, !pair && cl == 1 && persistent_default());
+  CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride, cw);
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh) * kw * C_in, uint64_t(kh) * kw * C_in, bn / cl, cw);
   IgemmParams p{};
   p.M = M; p.N = C_out;
   p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
   p.num_k_blocks = kh * kw * p.cblocks;
+  p.taps_total = kh * kw;
+  if (cw != IG_BLOCK_K) {
+    p.cw = cw;
+    p.num_k_blocks = (kh * kw + IG_BLOCK_K / cw - 1) / (IG_BLOCK_K / cw);
+  }
   p.taps_w = kw; p.b_cols_per_tap = C_in; p.is_conv = 1;
   p.HW_out = H_out * W_out; p.W_out = W_out;
   p.stride = stride; p.pad = pad; p.dil = dil;
@@ -613,6 +633,56 @@ void conv2d_nhwc_shuffle_tf32(const float* x, const float* w, float* out, int NB
     throw;
   }
   g_out_map_override = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-dilation convolution: `branches` convolutions of the SAME input with the same kh x kw / stride but their own dilation and
+// padding, each producing its own slice of the output channels, as ONE implicit GEMM (IgemmParams::ms_*): filter rows are
+// (branch, row) pairs, the weight matrix w [C_out_total, branches * kh, kw, C_in] is block diagonal.  The CPC encoder's five
+// dilated 4x4 / stride-2 stem convolutions (/root/reference/src/simple_models.py:441-451, :455-460) + bias + ELU + concatenation.
+// ------------------------------------------------------------------------------------------------
+bool conv_multidil_supported(int H_out, int W_out, int C_in, int stride, int branches) {
+  if (branches < 1 || branches > 8) return false;
+  if (!conv_geometry_supported(H_out, W_out, C_in, stride)) return false;
+  return !(env_int("FEDB200_KPS", 2) == 1 || env_int("FEDB200_PERSIST", 1) == 0 || env_int("FEDB200_CLUSTER", 1) != 1 ||
+           env_int("FEDB200_2CTA", 0) != 0);
+}
+
+void conv2d_nhwc_multidil_tf32(const float* x, const float* w, const float* bias, int act, float* y, int NB, int H, int W, int C_in,
+                               int C_out, int branches, int kh, int kw, int stride, const int* dils, const int* pads, int H_out,
+                               int W_out, cudaStream_t stream) {
+  if (!conv_multidil_supported(H_out, W_out, C_in, stride, branches))
+    throw std::runtime_error("fedb200: multi-dilation convolution not supported for this shape");
+  const int rows = 128 / W_out;
+  const int boxH = rows <= H_out ? rows : H_out;
+  const int boxN = rows <= H_out ? 1 : rows / H_out;
+  const int M = NB * H_out * W_out;
+  const int bn = pick_block_n(M, C_out);
+  const int kh_all = branches * kh;
+  const int cw = pick_tap_pack(C_in, true);
+  CUtensorMap ta = make_tmap_nhwc(x, NB, H, W, C_in, boxN, boxH, W_out, stride, cw);
+  CUtensorMap tb = make_tmap_2d(w, C_out, uint64_t(kh_all) * kw * C_in, uint64_t(kh_all) * kw * C_in, bn, cw);
+  IgemmParams p{};
+  p.M = M; p.N = C_out;
+  p.cblocks = (C_in + IG_BLOCK_K - 1) / IG_BLOCK_K;
+  p.num_k_blocks = kh_all * kw * p.cblocks;
+  p.taps_total = kh_all * kw;
+  if (cw != IG_BLOCK_K) {
+    p.cw = cw;
+    p.num_k_blocks = (kh_all * kw + IG_BLOCK_K / cw - 1) / (IG_BLOCK_K / cw);
+  }
+  p.taps_w = kw; p.b_cols_per_tap = C_in; p.is_conv = 1;
+  p.HW_out = H_out * W_out; p.W_out = W_out;
+  p.stride = stride; p.pad = 0; p.dil = 1;
+  p.out = y; p.ldo = C_out; p.bias = bias; p.act = act; p.stats = nullptr;
+  p.k_splits = 1; p.kb_per_split = p.num_k_blocks; p.dbg = env_int("FEDB200_DBG", 0);
+  p.ms_kh = kh;
+  for (int b = 0; b < branches; ++b) {
+    if (dils[b] < 1 || dils[b] > 255 || pads[b] < 0 || pads[b] > 255) throw std::runtime_error("fedb200: multi-dilation: dilation / padding out of range");
+    p.ms_dil |= (unsigned long long)(dils[b]) << (8 * b);
+    p.ms_pad |= (unsigned long long)(pads[b]) << (8 * b);
+  }
+  dispatch_p(bn, ta, tb, p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

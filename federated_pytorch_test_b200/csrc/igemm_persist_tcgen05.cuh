@@ -123,6 +123,19 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         int cb = c.kb_begin - tap * p.cblocks;
         int r = tap / p.taps_w, sx = tap - r * p.taps_w;
         int left = c.kb_count, kb = c.kb_begin;
+        const int cwp = (p.cw == 8 || p.cw == 16) ? p.cw : 0;      // tap packing
+        const int tpk = cwp ? IG_BLOCK_K / cwp : 1;
+        // tap -> offset inside the (padded) input window
+        auto tap_offset = [&](int rr_, int sx_, int& cw_, int& ch_) {
+          cw_ = sx_ * p.dil - p.pad;
+          ch_ = rr_ * p.dil;
+          if (p.ms_kh > 0) {                                        // multi-dilation: rows are (branch, row) pairs
+            const int br = rr_ / p.ms_kh, rr = rr_ - br * p.ms_kh;
+            const int d = int((p.ms_dil >> (8 * br)) & 0xffull), pd = int((p.ms_pad >> (8 * br)) & 0xffull);
+            cw_ = sx_ * d - pd;
+            ch_ = rr * d - pd;
+          }
+        };
         while (left > 0) {
           const int nk = left < KPS ? left : KPS;
           left -= nk;
@@ -137,19 +150,36 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
               if (j < nk) {
                 uint8_t* a_dst = dst + j * S::KB_BYTES;
                 uint8_t* b_dst = a_dst + S::A_BYTES;
+                if (cwp) {
+                  // tpk taps per k-block, each a [128 rows x cwp channels] sub-tile of A and a [BLOCK_N x cwp] sub-tile of B
+                  const int sub_a = IG_BLOCK_M * cwp * 4, sub_b = BLOCK_N * cwp * 4;
+                  for (int jt = 0; jt < tpk; ++jt) {
+                    const int tp = (kb + j) * tpk + jt;
+                    const bool real = tp < p.taps_total;
+                    int cw = 0, ch = 0;
+                    if (real) tap_offset(tp / p.taps_w, tp % p.taps_w, cw, ch);
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  if (p.is_conv)
-                    tma_load_4d(a_dst + mt * S::A_TILE_BYTES, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, sx * p.dil - p.pad,
-                                h0[mt] + r * p.dil, img[mt]);
-                  else
-                    tma_load_2d(a_dst + mt * S::A_TILE_BYTES, &tmap_a, &full_bar[s], (kb + j) * IG_BLOCK_K,
-                                c.m0 + mt * IG_BLOCK_M);
-                }
-                tma_load_2d(b_dst, &tmap_b, &full_bar[s], (r * p.taps_w + sx) * p.b_cols_per_tap + cb * IG_BLOCK_K, c.n0);
-                if (++cb == p.cblocks) {
-                  cb = 0;
-                  if (++sx == p.taps_w) { sx = 0; ++r; }
+                    for (int mt = 0; mt < MT; ++mt)          // a tap past the filter: image index out of range -> zeros
+                      tma_load_4d(a_dst + mt * S::A_TILE_BYTES + jt * sub_a, &tmap_a, &full_bar[s], 0, cw, h0[mt] + ch,
+                                  real ? img[mt] : 0x3fffffff);
+                    tma_load_2d(b_dst + jt * sub_b, &tmap_b, &full_bar[s], real ? tp * p.b_cols_per_tap : 0x3fffffff, c.n0);
+                  }
+                } else {
+                  int cw, ch;
+                  tap_offset(r, sx, cw, ch);
+#pragma unroll
+                  for (int mt = 0; mt < MT; ++mt) {
+                    if (p.is_conv)
+                      tma_load_4d(a_dst + mt * S::A_TILE_BYTES, &tmap_a, &full_bar[s], cb * IG_BLOCK_K, cw, h0[mt] + ch, img[mt]);
+                    else
+                      tma_load_2d(a_dst + mt * S::A_TILE_BYTES, &tmap_a, &full_bar[s], (kb + j) * IG_BLOCK_K,
+                                  c.m0 + mt * IG_BLOCK_M);
+                  }
+                  tma_load_2d(b_dst, &tmap_b, &full_bar[s], (r * p.taps_w + sx) * p.b_cols_per_tap + cb * IG_BLOCK_K, c.n0);
+                  if (++cb == p.cblocks) {
+                    cb = 0;
+                    if (++sx == p.taps_w) { sx = 0; ++r; }
+                  }
                 }
               }
             }
@@ -164,7 +194,18 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(/*tf32*/ 2, IG_BLOCK_M, BLOCK_N);
     if (elect_one()) {
-      const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(tiles));
+      // operand rows of 128 bytes (one tap x 32 channels per k-block) or, with tap packing, cw * 4 bytes per sub-tile
+      const uint32_t cwq = (p.cw == 8 || p.cw == 16) ? uint32_t(p.cw) : uint32_t(IG_BLOCK_K);
+      const uint64_t desc0 = make_kmajor_desc(smem_u32(tiles), cwq * 4u);
+      const uint32_t mma_per_sub = cwq / IG_UMMA_K;                          // MMAs (K = 8) per sub-tile: 1, 2 or 4
+      const uint32_t sub_a16 = (IG_BLOCK_M * cwq * 4u) >> 4, sub_b16 = (uint32_t(BLOCK_N) * cwq * 4u) >> 4;
+      uint64_t a_off[IG_BLOCK_K / IG_UMMA_K], b_off[IG_BLOCK_K / IG_UMMA_K];   // descriptor offsets of the four MMAs of a k-block
+#pragma unroll
+      for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
+        const uint32_t sub = uint32_t(k) / mma_per_sub, in = uint32_t(k) - sub * mma_per_sub;
+        a_off[k] = uint64_t(sub * sub_a16 + 2u * in);
+        b_off[k] = uint64_t(sub * sub_b16 + 2u * in);
+      }
       int s = 0;
       uint32_t ph = 0;
       int j_tile = 0;
@@ -193,9 +234,9 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 for (int k = 0; k < IG_BLOCK_K / IG_UMMA_K; ++k) {
 #pragma unroll
                   for (int mt = 0; mt < MT; ++mt) {
-                    const uint64_t ad = adesc + uint64_t(mt * (S::A_TILE_BYTES >> 4) + 2 * k);
-                    if (j == 0 && k == 0) umma_tf32(d_tmem + mt * BLOCK_N, ad, bdesc, idesc, first ? 0u : 1u);
-                    else umma_tf32_acc(d_tmem + mt * BLOCK_N, ad, bdesc + uint64_t(2 * k), idesc);
+                    const uint64_t ad = adesc + uint64_t(mt * (S::A_TILE_BYTES >> 4)) + a_off[k];
+                    if (j == 0 && k == 0) umma_tf32(d_tmem + mt * BLOCK_N, ad, bdesc + b_off[k], idesc, first ? 0u : 1u);
+                    else umma_tf32_acc(d_tmem + mt * BLOCK_N, ad, bdesc + b_off[k], idesc);
                   }
                 }
               }

@@ -49,6 +49,16 @@ struct IgemmParams {
   int accumulate;        // persistent kernel: out += result (bulk reduce-add / atomics) instead of out = result; no memset
   int tma_store;         // persistent kernel: write the output with bulk tensor stores / reduce-adds (needs ldo % 4 == 0)
   long long* trace;      // optional [16] clock64 stamps of CTA 0 (tools/trace_conv.py); nullptr in production
+  int cw;                // persistent kernel, convolutions with few input channels: channels per filter tap inside a 32-wide
+                         // k-block.  0 / 32 = one tap per k-block (C_in padded to 32 by the TMA zero fill: 4x wasted MMAs at C_in = 8);
+                         // 8 / 16 = "tap packing": a k-block holds 32 / cw taps, each its own cw-channel sub-tile (rows of cw * 4 bytes,
+                         // TMA SWIZZLE_32B / 64B, UMMA descriptors of the matching layout).  num_k_blocks = ceil(taps / (32 / cw)).
+  int taps_total;        // kh * kw (tap packing: taps beyond it load out-of-bounds zeros)
+  int ms_kh;             // persistent kernel, > 0: "multi-dilation" convolution — the filter rows are ms_branches groups of ms_kh rows,
+                         // group b reads the input with dilation ms_dil[b] and padding ms_pad[b] (one byte each, packed); the weight
+                         // matrix is block diagonal (branch b owns its own output channels).  The five dilated stem convolutions
+                         // of the CPC encoder run as ONE launch writing the concatenated tensor.  pad = 0, dil = 1 then.
+  unsigned long long ms_dil, ms_pad;
   int shuffle_ci;        // persistent kernel, > 0: the N columns are (ph, pw, ci) phase-packed channels of a stride-2 data gradient /
                          // transposed conv; each 32 x 32 chunk is stored to out[n, 2 ho + ph, 2 wo + pw, ci0 .. ci0 + 31] through a
                          // 5-D tensor map (no separate pixel-shuffle pass).  shuffle_ci = channels of the shuffled output.

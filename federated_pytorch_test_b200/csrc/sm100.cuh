@@ -271,6 +271,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same for rows of `sw` = 32 / 64 / 128 bytes (TMA SWIZZLE_32B / 64B / 128B): SBO = 8 rows * sw, layout type 6 / 4 / 2.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sw) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8u * sw) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(sw == 128u ? 2u : (sw == 64u ? 4u : 6u)) << 61;
+  return d;
+}
 // Instruction descriptor: fp32 accumulate, A/B format (1 = bf16, 2 = tf32), both K-major, tile M x N.
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_format, uint32_t M, uint32_t N) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

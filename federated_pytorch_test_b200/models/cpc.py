@@ -3,9 +3,9 @@
 Behavioural spec: /root/reference/src/simple_models.py:436-514
 (``EncoderCNN`` 16 tensors, ``ContextgenCNN`` 4, ``PredictorCNN`` 2).
 
-The five dilated stem convolutions read the same input tile and their outputs
-are concatenated on the channel axis; here they are evaluated through
-:func:`ops.functional.conv_act` branch by branch and concatenated.
+The five dilated stem convolutions read the same input and their outputs are
+concatenated on the channel axis: :func:`ops.functional.dilated_stem` runs them
+as one tcgen05 launch that writes the concatenated tensor.
 """
 from __future__ import annotations
 
@@ -34,8 +34,7 @@ class EncoderCNN(BlockPartitioned):
         self.conv4 = nn.Conv2d(L // 2, L, 4, stride=2, padding=1)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        stem = [FX.conv_act(x, getattr(self, "conv1_%d" % d)) for d in _DILATIONS]
-        h = torch.cat(stem, dim=1)
+        h = FX.dilated_stem(x, [getattr(self, "conv1_%d" % d) for d in _DILATIONS])
         for name in ("conv2", "conv3", "conv4"):
             h = FX.conv_act(h, getattr(self, name))
         return FX.global_avg_pool(h) if (h.shape[2] == 2 and h.shape[3] == 2 and h.shape[0] > 1) else F.avg_pool2d(h, 2).squeeze()

@@ -573,6 +573,98 @@ class _ConvAct(torch.autograd.Function):
         return dx, dw, (db if need_b else None), None, None, None, None
 
 
+def _conv_out(size: int, k: int, s: int, p: int, d: int) -> int:
+    return (size + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def dilated_stem_supported(x: torch.Tensor, convs) -> bool:
+    """Several convolutions of the SAME input that differ only in dilation / padding (and own their output channels), followed
+    by a channel concatenation: the CPC encoder stem (/root/reference/src/simple_models.py:441-451, :455-460)."""
+    if not CONV_ACT or len(convs) < 2 or len(convs) > 8 or x.dim() != 4 or x.dtype != torch.float32 or not x.is_cuda:
+        return False
+    c0 = convs[0]
+    k, st = c0.kernel_size[0], c0.stride[0]
+    outs = set()
+    for c in convs:
+        if not isinstance(c, nn.Conv2d) or isinstance(c, nn.ConvTranspose2d) or c.groups != 1 or isinstance(c.padding, str):
+            return False
+        if tuple(c.kernel_size) != (k, k) or tuple(c.stride) != (st, st) or c.in_channels != c0.in_channels \
+                or c.out_channels != c0.out_channels or (c.bias is None) != (c0.bias is None):
+            return False
+        if c.padding[0] != c.padding[1] or c.dilation[0] != c.dilation[1] or c.dilation[0] > 255 or c.padding[0] > 255:
+            return False
+        outs.add((_conv_out(x.shape[2], k, st, c.padding[0], c.dilation[0]), _conv_out(x.shape[3], k, st, c.padding[0], c.dilation[0])))
+    if len(outs) != 1 or c0.in_channels % 4 or (c0.out_channels * len(convs)) % 4:
+        return False
+    Ho, Wo = next(iter(outs))
+    return Ho > 0 and Wo > 0 and bool(ext().conv_multidil_supported(Ho, Wo, c0.in_channels, st, len(convs)))
+
+
+class _DilatedStem(torch.autograd.Function):
+    """``cat([ELU?(conv_b(x)) for b], 1)`` as ONE tcgen05 implicit GEMM: the filter rows of the launch are (branch, row) pairs,
+    every branch reads the input through its own dilation / padding (IgemmParams::ms_*), the block-diagonal weight matrix sends
+    branch b to its own output channels, bias + ELU in the epilogue, one bulk tensor store per chunk of the concatenated tensor.
+    Backward: one bias+ELU' pass over the concatenated gradient, one tcgen05 weight-gradient launch per branch."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        k, st, dils, pads, act, has_bias = cfg
+        e = ext()
+        xn = _nhwc(x)
+        B = len(dils)
+        ws = params[0::2]
+        Co, Ci = ws[0].shape[0], ws[0].shape[1]
+        w_all = torch.stack([w.permute(0, 2, 3, 1) for w in ws])                 # [B, Co, k, k, Ci]
+        wm = torch.zeros(B, Co, B, k, k, Ci, dtype=torch.float32, device=x.device)
+        wm.diagonal(dim1=0, dim2=2).copy_(w_all.permute(1, 2, 3, 4, 0))          # branch b -> rows (b, :) of its own channels
+        bias = torch.cat([b for b in params[1::2]]) if has_bias else None
+        Ho = _conv_out(xn.shape[1], k, st, pads[0], dils[0])
+        Wo = _conv_out(xn.shape[2], k, st, pads[0], dils[0])
+        out = e.conv2d_nhwc_multidil(xn, wm.view(B * Co, B * k, k, Ci), bias, bool(act), k, st, list(dils), list(pads), Ho, Wo)
+        ctx.save_for_backward(xn, out)
+        ctx.cfg = cfg
+        ctx.params = params
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xn, out = ctx.saved_tensors
+        k, st, dils, pads, act, has_bias = ctx.cfg
+        params = ctx.params
+        B = len(dils)
+        Co, Ci = params[0].shape[0], params[0].shape[1]
+        need_b = has_bias and any(ctx.needs_input_grad[3 + 2 * b] for b in range(B))
+        dz, db = _act_bwd_bias(_nhwc(dout), out, act, need_b, None)              # [N, Ho, Wo, B * Co], [B * Co]
+        N, Ho, Wo, _ = dz.shape
+        dzb = dz.view(N, Ho, Wo, B, Co).permute(3, 0, 1, 2, 4).contiguous()      # one pass -> B contiguous [N, Ho, Wo, Co] slabs
+        grads = []
+        dx = None
+        for b in range(B):
+            w, bp = params[2 * b], params[2 * b + 1]
+            dw = None
+            if ctx.needs_input_grad[2 + 2 * b]:
+                if conv_wgrad_supported(xn, dzb[b], st):
+                    dw = conv_wgrad(xn, dzb[b], k, k, Ci, st, pads[b], dils[b], w)
+                else:
+                    dw = torch.ops.aten.convolution_backward(dzb[b].permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), w, None, [st, st],
+                                                             [pads[b]] * 2, [dils[b]] * 2, False, [0, 0], 1, [False, True, False])[1]
+            if ctx.needs_input_grad[0]:      # the stem reads data: not needed in the drivers; ATen keeps the op differentiable
+                g = torch.ops.aten.convolution_backward(dzb[b].permute(0, 3, 1, 2), xn.permute(0, 3, 1, 2), w, None, [st, st],
+                                                        [pads[b]] * 2, [dils[b]] * 2, False, [0, 0], 1, [True, False, False])[0]
+                dx = g if dx is None else dx + g
+            grads += [dw, db[b * Co:(b + 1) * Co] if (need_b and bp is not None and ctx.needs_input_grad[3 + 2 * b]) else None]
+        return (dx, None, *grads)
+
+
+def dilated_stem(x: torch.Tensor, convs, act: bool = True) -> torch.Tensor:
+    cfg = (convs[0].kernel_size[0], convs[0].stride[0], tuple(c.dilation[0] for c in convs), tuple(c.padding[0] for c in convs),
+           bool(act), convs[0].bias is not None)
+    params = []
+    for c in convs:
+        params += [c.weight, c.bias]
+    return _DilatedStem.apply(x, cfg, *params)
+
+
 def conv_transpose_act_supported(x: torch.Tensor, conv: nn.Module) -> bool:
     """ConvTranspose2d(k=4, stride=2, padding=1) of the VAE decoders as one 3x3 convolution with 4*C_out
     phase channels + pixel shuffle (conv_math.pack_convT_s2_weight)."""
@@ -644,6 +736,32 @@ def conv1x1_linear(x: torch.Tensor, conv: nn.Conv2d, act: bool) -> torch.Tensor:
     return out.view(N, H, W, conv.out_channels).permute(0, 3, 1, 2)
 
 
+def unfold_conv_supported(x: torch.Tensor, conv: nn.Module) -> bool:
+    """Stride-1 convolutions on tiny maps with many channels (the 2x2 convolutions of the CPC context network on its 3x3 / 4x4
+    latent grid): im2col rows [N * Ho * Wo, Ci * k * k] x the dense-layer GEMM kernel with the bias + ELU epilogue.
+    Measured before (direct-convolution kernel, `profiles/r2/r2_call14.log`): 254 us forward / 420 us data gradient for a 75 MFLOP layer."""
+    if not (CONV_ACT and LINEAR_F32) or not isinstance(conv, nn.Conv2d) or isinstance(conv, nn.ConvTranspose2d):
+        return False
+    if x.dim() != 4 or x.dtype != torch.float32 or conv.groups != 1 or conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+        return False
+    if tuple(conv.stride) != (1, 1) or tuple(conv.dilation) != (1, 1):
+        return False
+    kh, kw = conv.kernel_size
+    Ho, Wo = x.shape[2] + 2 * conv.padding[0] - kh + 1, x.shape[3] + 2 * conv.padding[1] - kw + 1
+    return Ho >= 1 and Wo >= 1 and Ho * Wo <= 64 and conv.in_channels * kh * kw >= 64
+
+
+def unfold_conv(x: torch.Tensor, conv: nn.Conv2d, act: bool) -> torch.Tensor:
+    N, C, H, W = x.shape
+    kh, kw = conv.kernel_size
+    Ho, Wo = H + 2 * conv.padding[0] - kh + 1, W + 2 * conv.padding[1] - kw + 1
+    # im2col as ONE strided copy (F.unfold launches an im2col kernel per sample: 1024 launches per two CPC steps, r2_call15.log)
+    xp = F.pad(x, (conv.padding[1], conv.padding[1], conv.padding[0], conv.padding[0])) if (conv.padding[0] or conv.padding[1]) else x
+    rows = xp.unfold(2, kh, 1).unfold(3, kw, 1).permute(0, 2, 3, 1, 4, 5).reshape(N * Ho * Wo, C * kh * kw)
+    out = _LinearAct.apply(rows, conv.weight.reshape(conv.out_channels, C * kh * kw), conv.bias, bool(act))
+    return out.view(N, Ho, Wo, conv.out_channels).permute(0, 3, 1, 2)
+
+
 def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor:
     if isinstance(conv, nn.ConvTranspose2d):
         return _ConvTransposeAct.apply(x, conv.weight, conv.bias, bool(act))
@@ -682,7 +800,7 @@ def _dense_wgrad(dz: torch.Tensor, x: torch.Tensor, wparam) -> Optional[torch.Te
     """dW [N, K] = dz^T x in true fp32: accumulated into ``wparam.grad`` when allowed (returns None), else returned."""
     e = ext()
     N, K = dz.shape[1], x.shape[1]
-    if _ACC_INTO_GRAD["on"] and wparam is not None and getattr(wparam, "grad", None) is not None \
+    if _ACC_INTO_GRAD["on"] and wparam is not None and wparam.is_leaf and wparam.grad is not None \
             and wparam.grad.is_contiguous() and tuple(wparam.grad.shape) == (N, K):
         e.linear_f32_wgrad(dz, x, wparam.grad, True)
         return None

@@ -96,10 +96,24 @@ def conv_act(x: torch.Tensor, conv: nn.Module, act: bool = True) -> torch.Tensor
             return cuda_ops.conv_act(x, conv, act)
         if cuda_ops.conv1x1_supported(x, conv):
             return cuda_ops.conv1x1_linear(x, conv, act)
+        if cuda_ops.unfold_conv_supported(x, conv):
+            return cuda_ops.unfold_conv(x, conv, act)
         if cuda_ops.smallconv_supported(x, conv):
             return cuda_ops.small_conv(x, conv, act, False)
     y = conv(x)
     return F.elu(y) if act else y
+
+
+def dilated_stem(x: torch.Tensor, convs, act: bool = True) -> torch.Tensor:
+    """``cat([ELU?(conv(x)) for conv in convs], 1)`` for convolutions that differ only in dilation / padding — the five-branch
+    stem of the CPC encoder (/root/reference/src/simple_models.py:455-460).  On B200 ONE tcgen05 launch reads the input once per
+    tap and writes the concatenated tensor (cuda_ops._DilatedStem); elsewhere branch by branch."""
+    if _use_fast(x):
+        from . import cuda_ops
+
+        if cuda_ops.dilated_stem_supported(x, convs):
+            return cuda_ops.dilated_stem(x, list(convs), act)
+    return torch.cat([conv_act(x, c, act) for c in convs], dim=1)
 
 
 def conv_act_pool(x: torch.Tensor, conv: nn.Conv2d, act: bool = True, pool: bool = False) -> torch.Tensor:

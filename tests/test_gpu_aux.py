@@ -167,6 +167,26 @@ def test_small_direct_conv_forward_backward(B, Ci, H, Co, k, pad, act, pool):
     assert rel_err(gx, rx) < 1e-4 and rel_err(gw, rw) < 1e-4 and rel_err(gb, rb) < 1e-4
 
 
+@pytest.mark.parametrize("B,Ci,H,Co,k,pad,act", [(128, 64, 3, 64, 2, 1, True), (128, 64, 4, 128, 2, 0, True), (16, 256, 3, 64, 2, 1, False),
+                                                 (9, 32, 5, 24, 3, 1, True)])
+def test_unfold_gemm_conv_forward_backward(B, Ci, H, Co, k, pad, act):
+    """2x2 / 3x3 convolutions on the CPC latent grid: im2col rows x fp32 GEMM kernel (true fp32 -> tight tolerance)."""
+    torch.manual_seed(B + Ci + H + Co)
+    conv = nn.Conv2d(Ci, Co, k, padding=pad, bias=(B != 16)).to(DEV)
+    x = torch.randn(B, Ci, H, H, device=DEV, requires_grad=True)
+    assert cuda_ops.unfold_conv_supported(x, conv)
+    n0 = cuda_ops.launch_count()
+    y = cuda_ops.unfold_conv(x, conv, act)
+    assert cuda_ops.launch_count() - n0 == 1           # the GEMM kernel (bias + ELU in its epilogue)
+    ref = F.conv2d(x.double(), conv.weight.double(), conv.bias.double() if conv.bias is not None else None, 1, pad)
+    ref = F.elu(ref) if act else ref
+    assert y.shape == ref.shape and rel_err(y.double(), ref) < 1e-5
+    g = torch.randn_like(y)
+    params = [x, conv.weight] + ([conv.bias] if conv.bias is not None else [])
+    for u, v in zip(torch.autograd.grad(y, params, g), torch.autograd.grad(ref, params, g.double())):
+        assert rel_err(u.double(), v) < 1e-4
+
+
 def _twin_grads(factory, inputs, loss_fn, tol, ref_double=False):
     """Same module twice; one stepped on the fast path, one on the ATen path (optionally in fp64: cuDNN's fp32 convolutions
     may still multiply in TF32); compares loss and every parameter gradient."""
@@ -209,37 +229,42 @@ def _l2_err(u, v):
     return float((u.double() - v.double()).norm() / v.double().norm().clamp_min(1e-30))
 
 
-def test_net2_fast_path_no_worse_than_library_tf32():
-    """Net2's convolutions run on the TF32 tensor cores (ours: tcgen05; ATen: cuDNN, TF32 allowed by default), and a TF32-sized
-    perturbation flips max-pool winners, so neither agrees with an fp64 oracle to better than a few per cent in the conv
-    gradients.  The yardstick is therefore the library itself: against the fp64 oracle our error must stay within 3x the
-    ATen/cuDNN TF32 error (+1e-2), and the loss within 5e-3."""
+def test_net2_fast_path_vs_fp64_oracles():
+    """Net2's convolutions run on the TF32 tensor cores.  A plain fp64 oracle disagrees with that by MORE than TF32's 2^-11:
+    the operand rounding flips ~0.02 % of the 2x2 max-pool winners (measured per stage: 92 / 68 / 42 / 11 windows at batch 32,
+    tools/diag_net2_tf32.py, profiles/r2/r2_call14.log) and every flip moves one term of the upstream gradients, which shows up
+    as 2-6 % relative L2 error in the conv weight gradients while everything downstream of the last pool (conv4.bias, fc*) agrees
+    to 5e-4.  An oracle that rounds the conv operands to TF32 (round-to-nearest) removes 2/3 of that.  (ATen / cuDNN on this
+    image does not take a plain-TF32 path for these shapes — its error against fp64 is 1e-4 — so it is no yardstick either.)
+    Bounds here: a wrong tap / layout / missing term would be an O(1) error; the kernels themselves are pinned at 3e-3 by the
+    layer-level tests (conv + bias + ELU forward / dgrad / wgrad, NHWC max-pool, dense layers)."""
+    from federated_pytorch_test_b200.utils.tf32_oracle import tf32_conv_oracle
     torch.manual_seed(1000)
     x = torch.randn(32, 3, 32, 32, device=DEV)
     y = torch.randint(0, 10, (32,), device=DEV)
     torch.manual_seed(0)
     a = models.Net2().to(DEV)
-    b = models.Net2().to(DEV)
-    o = models.Net2().to(DEV)
-    b.load_state_dict(a.state_dict())
-    o.load_state_dict(a.state_dict())
-    o = o.double()
     FX.set_fast_path(True)
     la = losses.cross_entropy(a(x), y)
     la.backward()
-    FX.set_fast_path(False)
-    lb = losses.cross_entropy(b(x), y)
-    lb.backward()
-    lo = losses.cross_entropy(o(x.double()), y)
-    lo.backward()
-    FX.set_fast_path(True)
-    assert float(la) == pytest.approx(float(lo), rel=5e-3)
-    report = {}
-    for (n, pa), (_, pb), (_, po) in zip(a.named_parameters(), b.named_parameters(), o.named_parameters()):
-        report[n] = (_l2_err(pa.grad, po.grad), _l2_err(pb.grad, po.grad))
-    print("Net2 gradient L2 errors vs fp64 (ours, ATen TF32):", {n: "%.1e / %.1e" % v for n, v in report.items()})
-    bad = {n: v for n, v in report.items() if not v[0] <= 3 * v[1] + 1e-2}
-    assert not bad, "ours vs library TF32 error against the fp64 oracle: %s" % report
+    errs = {}
+    for mode in ("fp64", "rna"):
+        o = models.Net2().to(DEV)
+        o.load_state_dict(a.state_dict())
+        o = o.double()
+        if mode == "rna":
+            tf32_conv_oracle(o, "rna")
+        FX.set_fast_path(False)
+        lo = losses.cross_entropy(o(x.double()), y)
+        lo.backward()
+        FX.set_fast_path(True)
+        assert float(la) == pytest.approx(float(lo), rel=1e-5)
+        errs[mode] = {n: _l2_err(pa.grad, po.grad) for (n, pa), (_, po) in zip(a.named_parameters(), o.named_parameters())}
+    print("Net2 gradient L2 errors:", {n: "%.1e (fp64) %.1e (tf32-rna)" % (errs["fp64"][n], errs["rna"][n]) for n in errs["fp64"]})
+    for n in errs["fp64"]:
+        after_last_pool = n.startswith("fc") or n == "conv4.bias"
+        assert errs["fp64"][n] < (2e-3 if after_last_pool else 0.12), (n, errs["fp64"][n])
+        assert errs["rna"][n] < (1e-3 if after_last_pool else 0.05), (n, errs["rna"][n])
 
 
 def test_vae_and_cpc_fast_path_match_aten():

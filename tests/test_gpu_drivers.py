@@ -58,18 +58,58 @@ def test_fedprox_lbfgs_resnet():
             assert float(p) == float(p) and float(d) == float(d)
 
 
+def test_lbfgs_graphed_closure_equals_eager():
+    """The L-BFGS closure replayed from CUDA graphs (gradient evaluation + line-search probe).  (a) On identical state a replay
+    and an eager evaluation give the same loss pair and the same block gradient; (b) a whole run walks the same iterates as
+    the eager run up to what L-BFGS makes of float-atomic summation order (two eager runs differ by the same amount)."""
+    kw = dict(K=2, Nloop=1, Nadmm=2, max_minibatches=4, check_results=False, model="Net", default_batch=32, optimizer="lbfgs")
+    ea, a = _run(fedprox_multi, **kw, graphs=False)
+    ea2, a2 = _run(fedprox_multi, **kw, graphs=False)
+    eb, b = _run(fedprox_multi, **kw, graphs=True)
+    assert eb.graph_replays > 0 and ea.graph_replays == 0
+
+    def residuals(lines):
+        return [tuple(float(v) for v in l.split("primal=")[1].split(" dual=")) for l in lines if l.startswith("block=[")]
+
+    ra, ra2, rb = residuals(a), residuals(a2), residuals(b)
+    assert len(ra) == len(rb) == 5 * 2
+    spread = max(abs(u - v) / max(abs(u), 1e-12) for x, y in zip(ra, ra2) for u, v in zip(x, y))     # eager vs eager
+    print("eager-vs-eager relative spread of the residuals: %.2e" % spread)
+    for (pa, da), (pb, db) in zip(ra, rb):
+        assert pa == pytest.approx(pb, rel=max(5e-2, 5 * spread), abs=1e-7) and da == pytest.approx(db, rel=max(5e-2, 5 * spread), abs=1e-7)
+    # (a): same state, replay vs eager body
+    ident, gc_ = eb._graphs[("lbfgs", eb.replicas[0].ck)]
+    assert gc_.graph[True] is not None and gc_.graph[False] is not None
+    g = gc_.rep.block_grad(gc_.visit)
+    for with_grad in (True, False):
+        out_graph = gc_.evaluate(with_grad).clone()
+        g_graph = g.clone()
+        with torch.enable_grad() if with_grad else torch.no_grad():
+            out_eager = gc_._body(with_grad).clone()
+        torch.testing.assert_close(out_graph, out_eager, rtol=1e-5, atol=1e-6)
+        if with_grad:
+            torch.testing.assert_close(g_graph, g.clone(), rtol=1e-4, atol=1e-6)
+
+
 def test_federated_vae_and_vae_cl_and_cpc(tmp_path):
     eng, lines = _run(federated_vae, K=2, Nloop=1, Nadmm=1, max_minibatches=2, be_verbose=False, graphs=True)
     _finite(lines, "dual (")
     eng, lines = _run(federated_vae_cl, K=2, Nloop=1, Nadmm=1, max_minibatches=1, be_verbose=False, default_batch=32,
                       Kc=4, Lc=8, graphs=False)
     assert len(_finite(lines, "dual (")) == 3
+    eng, lines = _run(federated_vae_cl, K=2, Nloop=1, Nadmm=1, max_minibatches=4, be_verbose=False, default_batch=32,
+                      Kc=4, Lc=8, graphs=True)          # L-BFGS closures (encoder / decoder blocks) replayed from CUDA graphs
+    assert len(_finite(lines, "dual (")) == 3 and eng.graph_replays > 0
     cfg = federated_cpc.Config(K=2, Lc=64, Rc=16, batch_size=8, Niter=2, load_model=False, init_model=True,
                                save_model=False, be_verbose=False, nbase=16, ckpt_dir=str(tmp_path), fast=True,
                                collective="fused", distributed=False, graphs=False)
     lines = []
     federated_cpc.run(cfg, log=lines.append)
     assert len(_finite(lines, "dual (N=")) == 4
+    cfg.graphs, cfg.Niter = True, 4
+    lines = []
+    eng = federated_cpc.run(cfg, log=lines.append)
+    assert len(_finite(lines, "dual (N=")) == 4 and eng.graph_replays > 0
 
 
 def test_federated_multi_fused_equals_torch_collective():

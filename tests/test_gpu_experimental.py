@@ -53,6 +53,35 @@ def test_conv_bias_act_forward_backward(B, H, Ci, Co, k, s, p, d, act):
     assert rel_err(gx, rx) < 5e-3 and rel_err(gw, rw) < 5e-3 and rel_err(gb, rb) < 5e-3
 
 
+# the five dilated stem convolutions of the CPC encoder as ONE launch writing the concatenated tensor (simple_models.py:455-460)
+@pytest.mark.parametrize("B,H,Ci,Co,dils", [(32, 32, 8, 8, (1, 2, 4, 8, 16)), (9, 32, 8, 8, (1, 2, 4, 8, 16)), (16, 32, 4, 12, (1, 3)),
+                                             (8, 16, 16, 8, (1, 2, 4))])
+@pytest.mark.parametrize("act", [True, False])
+def test_dilated_stem_one_launch(B, H, Ci, Co, dils, act):
+    from federated_pytorch_test_b200.ops import functional as FX
+    torch.manual_seed(B + H + Ci + Co)
+    convs = [nn.Conv2d(Ci, Co, 4, stride=2, dilation=d, padding=(3 * d) // 2).to(DEV) for d in dils]
+    x = torch.randn(B, Ci, H, H, device=DEV, requires_grad=True)
+    assert cuda_ops.dilated_stem_supported(x, convs)
+    n0 = cuda_ops.launch_count()
+    y = FX.dilated_stem(x, convs, act)
+    fwd_launches = cuda_ops.launch_count() - n0
+    params = [p for c in convs for p in (c.weight, c.bias)]
+    ref64 = torch.cat([F.conv2d(x.double(), c.weight.double(), c.bias.double(), 2, c.padding, c.dilation) for c in convs], 1)
+    ref64 = F.elu(ref64) if act else ref64
+    assert y.shape == ref64.shape
+    assert rel_err(y.double(), ref64) < 3e-3
+    # branch by branch on the same tensor-core path: same operand rounding, same products -> agreement to fp32 summation order
+    per_branch = torch.cat([cuda_ops.conv_act(x, c, act) for c in convs], 1)
+    assert rel_err(y, per_branch) < 1e-5
+    g = torch.randn_like(y)
+    got = torch.autograd.grad(y, [x] + params, g)
+    ref = torch.autograd.grad(ref64, [x] + params, g.double())
+    for u, v in zip(got, ref):
+        assert u.shape == v.shape and rel_err(u.double(), v) < 5e-3
+    assert fwd_launches == 1, "the stem must be one launch of our kernels, got %d" % fwd_launches
+
+
 # run with FEDB200_BN_BWD_FUSED=1: the binding then takes the single-kernel path for tensors that fit in registers
 @needs_bn_bwd_fused
 @pytest.mark.parametrize("C,M,res,act", [(256, 8192, False, True), (256, 8192, True, True), (512, 2048, True, True),

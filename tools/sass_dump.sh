@@ -19,7 +19,7 @@ declare -A KERNELS=(
   [bn_elu_fwd]='_ZN7fedb20017bn_elu_fwd_kernelEPKfPfS1_S1_S1_S2_S2_S2_S2_S2_iiffii'
   [bn_elu_bwd_reduce_1]='_ZN7fedb20024bn_elu_bwd_reduce_kernelILi1EEEvPKfS2_S2_S2_S2_S2_S2_Pfii'
   [bn_elu_bwd_apply_1]='_ZN7fedb20023bn_elu_bwd_apply_kernelILi1EEEvPKfS2_S2_S2_S2_S2_S2_S2_PfS3_S3_S3_ii'
-  [gemm_f32]='_ZN7fedb20015gemm_f32_kernelEPKfS1_S1_Pfiiixxxxiii'
+  [gemm_f32]='_ZN7fedb20015gemm_f32_kernelILi32ELi32EEEvPKfS2_S2_Pfiiixxxxiii'
   [info_nce_fwd]='_ZN7fedb20019info_nce_fwd_kernelEPKfS1_iiPfS2_S2_'
 )
 echo "# SASS listings (cuobjdump -sass, sm_100a, from $SO)" > $OUT/INDEX.md
