@@ -39,11 +39,17 @@ def run_aux_bench(args) -> dict:
         mod = federated_vae if args.driver == "vae" else federated_vae_cl
         task_cls = federated_vae.VAETask if args.driver == "vae" else federated_vae_cl.VAECLTask
         first = straddle_window(K, W, PRIME_STEPS, per_round)
-        rounds = -(-(first + K) // per_round) + 1
+        b_host = -(-(first + K) // per_round) * per_round           # first step served from pinned host memory (e2e window)
+        first_e = straddle_window(K, W, b_host, b_host + per_round)
+        rounds = -(-(first_e + K) // per_round) + 1 if not args.no_e2e else -(-(first + K) // per_round) + 1
         kw = dict(K=N, Nloop=1000, Nadmm=rounds, Nepoch=1, check_results=False, save_model=False, be_verbose=False,
                   graphs=not args.no_graphs, fast=not args.no_fast, collective=args.collective, max_minibatches=per_round, seed=69)
         cfg = mod.Config(**kw)
     last = first + K
+    e2e_on = args.driver != "cpc" and not args.no_e2e          # CPC draws synthetic LOFAR baselines on the device: no host path
+    if not e2e_on:
+        first_e = -1
+    last_e = first_e + K
     topo, coll = common.setup_runtime(cfg)
     task = task_cls(cfg, topo)
     ecfg = common.engine_config(cfg, Nepoch=1, diagnostics="pre") if args.driver == "cpc" else common.engine_config(cfg)
@@ -55,8 +61,40 @@ def run_aux_bench(args) -> dict:
     if sampler:
         sampler.start()          # early: NVML start-up stalls launches on every GPU of the box (see bench.py)
 
+    ev_e = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    slots = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)] if dev.type == "cuda" else None
+    slot_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    pending = []
+
+    def to_host_loaders():
+        from federated_pytorch_test_b200.data.cifar import CifarData
+
+        d = task.data
+        task.data = CifarData(d.train_images.cpu(), d.train_labels.cpu(), d.test_images.cpu(), d.test_labels.cpu()).to(dev, pin=True)
+        task._loaders.clear()
+
     def hook(e: Engine):
         n = e.steps_done
+        if e2e_on and first_e <= n - 1 < last_e and e.last_loss1 is not None:      # the step just finished was an e2e step
+            i = n & 1
+            slots[i].copy_(e.last_loss1.detach().reshape(()), non_blocking=True)     # D2H of this step's result
+            slot_ev[i].record()
+            pending.append(i)
+            while len(pending) > (0 if n >= last_e else 1):                          # read the previous step's value
+                j = pending.pop(0)
+                slot_ev[j].synchronize()
+                st["loss"] = float(slots[j])
+        if e2e_on and n == first_e:
+            topo.barrier()
+            torch.cuda.synchronize(dev)
+            st.update(te0=time.perf_counter(), ae0=e.aggregations_done)
+            ev_e[0].record()
+        elif e2e_on and n == last_e:
+            ev_e[1].record()
+            torch.cuda.synchronize(dev)
+            topo.barrier()
+            st.update(te1=time.perf_counter(), aggs_e=e.aggregations_done - st["ae0"])
+            e.stop_requested = True
         if n == first:
             topo.barrier()
             torch.cuda.synchronize(dev)
@@ -69,7 +107,10 @@ def run_aux_bench(args) -> dict:
             topo.barrier()
             st.update(t1=time.perf_counter(), launches=(cuda_ops.launch_count() - st["l0"]) + (e.graph_kernel_launches - st["g0"]),
                       aggs=e.aggregations_done - st["a0"], clocks=sampler.window(st["smi0"], sampler.mark()) if sampler else None)
-            e.stop_requested = True
+            if e2e_on:
+                to_host_loaders()          # from the next round on: pinned host memory -> native batch assembler -> async H2D
+            else:
+                e.stop_requested = True
 
     eng.step_hook = hook
     eng.run()
@@ -87,6 +128,16 @@ def run_aux_bench(args) -> dict:
                    "timed_steps": [first, last], "aggregations_in_window": st.get("aggs"), "collective": coll.name,
                    "cuda_graphs": bool(cfg.graphs), "wall_ms_per_step": wall / K,
                    "timing": "CUDA events, barrier+synchronize both sides, max over ranks"},
-        "clocks": st.get("clocks"), "gpu_launches": st.get("launches"), "e2e": None,
+        "clocks": st.get("clocks"), "gpu_launches": st.get("launches"),
+        "e2e": {"unavailable": "the CPC driver draws its synthetic LOFAR baselines on the device (the reference reads h5 files that do not exist here)"},
     }
+    if e2e_on:
+        ms_e = _max_over_ranks(ev_e[0].elapsed_time(ev_e[1]), dev)
+        loader = task.loader(topo.local_workers[0])
+        out["e2e"] = {"value": batch * N * K / (ms_e / 1e3), "unit": out["unit"], "ms_per_step": ms_e / K,
+                      "wall_ms_per_step": _max_over_ranks((st["te1"] - st["te0"]) * 1e3, dev) / K,
+                      "h2d_bytes_per_step": loader.h2d_bytes_per_batch * (1 if loader.host_resident else 0), "d2h_bytes_per_step": 4,
+                      "timed_steps": [first_e, last_e], "aggregations_in_window": st.get("aggs_e"), "last_loss_read_by_host": st.get("loss"),
+                      "note": "same engine, dataset moved to pinned host memory after the device window: native batch assembler, async H2D of "
+                              "every uint8 batch, every step's loss copied D2H into pinned memory and read by the host one step later"}
     return out if topo.is_root else {}

@@ -193,6 +193,15 @@ Tensor weight_flip(Tensor w) {    // [Co,kh,kw,Ci] -> [Ci,kh,kw,Co], taps rotate
   return out;
 }
 
+Tensor convT_pack(Tensor w) {    // [Ci, Co, 4, 4] (any strides) -> [4 * Co, 3, 3, Ci]
+  CHECK_F32_CUDA(w);
+  TORCH_CHECK(w.dim() == 4 && w.size(2) == 4 && w.size(3) == 4, "convT_pack: ConvTranspose2d(k=4) weight expected");
+  c10::cuda::CUDAGuard guard(w.device());
+  auto out = torch::empty({4 * w.size(1), 3, 3, w.size(0)}, w.options().memory_format(c10::MemoryFormat::Contiguous));
+  fb::convT_pack(fptr(w), fptr_mut(out), (int)w.size(0), (int)w.size(1), w.stride(0), w.stride(1), w.stride(2), w.stride(3), cur_stream());
+  return out;
+}
+
 // ---------------------------------------------------------------------------------------------- tensor cores
 Tensor linear_tf32(Tensor x, Tensor w, c10::optional<Tensor> bias, bool act) {
   CHECK_F32_CUDA(x); CHECK_F32_CUDA(w); CHECK_CONTIG(x); CHECK_CONTIG(w);
@@ -635,6 +644,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("avgpool_nhwc", &avgpool_nhwc);
   m.def("avgpool_nhwc_bwd", &avgpool_nhwc_bwd);
   m.def("weight_flip", &weight_flip);
+  m.def("convT_pack", &convT_pack);
   m.def("linear_tf32", &linear_tf32);
   m.def("conv_supported", &conv_supported);
   m.def("probe_launch", &probe_launch);

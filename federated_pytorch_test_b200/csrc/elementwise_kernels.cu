@@ -644,4 +644,37 @@ void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, i
   check_launch("weight_krsc_flip");
 }
 
+// ConvTranspose2d(k = 4, stride 2, padding 1) weight [Ci, Co, 4, 4] (any strides) -> KRSC filter [4 * Co, 3, 3, Ci] of the equivalent
+// 3x3 / pad 1 convolution with phase-major output channels (ops/conv_math.py::pack_convT_s2_weight: output phase ph takes filter
+// rows 3, 1 at window positions 0, 1 and phase 1 rows 2, 0 at positions 1, 2; the other position is zero).  One launch instead
+// of a 36-way torch.stack (11 us each, 11 per VAE step: profiles/r2/r2_call14.log).
+__device__ __forceinline__ int convT_tap(int phase, int t) {
+  return phase == 0 ? (t == 0 ? 3 : (t == 1 ? 1 : -1)) : (t == 0 ? -1 : (t == 1 ? 2 : 0));
+}
+__global__ void __launch_bounds__(256)
+convT_pack_kernel(const float* __restrict__ w, float* __restrict__ out, int Ci, int Co, long long s_ci, long long s_co, long long s_r,
+                  long long s_s) {
+  pdl_prologue();
+  const size_t total = size_t(4) * Co * 9 * Ci;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int ci = int(i % Ci);
+    size_t t = i / Ci;
+    const int ts = int(t % 3);
+    t /= 3;
+    const int tr = int(t % 3);
+    t /= 3;
+    const int co = int(t % Co);
+    const int phase = int(t / Co);
+    const int r = convT_tap(phase >> 1, tr), sx = convT_tap(phase & 1, ts);
+    out[i] = (r >= 0 && sx >= 0) ? w[ci * s_ci + co * s_co + r * s_r + sx * s_s] : 0.f;
+  }
+}
+void convT_pack(const float* w, float* out, int Ci, int Co, long long s_ci, long long s_co, long long s_r, long long s_s, cudaStream_t s) {
+  const size_t total = size_t(4) * Co * 9 * Ci;
+  int grid = int((total + 255) / 256);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  launch_pdl(convT_pack_kernel, dim3(grid), dim3(256), 0, s, w, out, Ci, Co, s_ci, s_co, s_r, s_s);
+  check_launch("convT_pack");
+}
+
 }  // namespace fedb200

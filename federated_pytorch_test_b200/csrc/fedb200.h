@@ -115,6 +115,8 @@ void head_bwd(const float* dlogits, const float* w, float* dx, int NB, int HW, i
 void avgpool_nhwc(const float* x, float* out, int NB, int HW, int C, cudaStream_t s);
 void avgpool_nhwc_bwd(const float* dout, float* dx, int NB, int HW, int C, cudaStream_t s);
 void weight_krsc_flip(const float* w, float* out, int C_out, int C_in, int kh, int kw, cudaStream_t s);
+// ConvTranspose2d(4, 2, 1) weight [Ci, Co, 4, 4] (strided) -> phase-packed KRSC filter [4 * Co, 3, 3, Ci]
+void convT_pack(const float* w, float* out, int Ci, int Co, long long s_ci, long long s_co, long long s_r, long long s_s, cudaStream_t s);
 
 // ---- losses (loss_kernels.cu) --------------------------------------------------------------------
 void cross_entropy_fwd(const float* logits, const long long* labels, float* loss, float* probs, int B, int C,

@@ -125,6 +125,8 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         int left = c.kb_count, kb = c.kb_begin;
         const int cwp = (p.cw == 8 || p.cw == 16) ? p.cw : 0;      // tap packing
         const int tpk = cwp ? IG_BLOCK_K / cwp : 1;
+        const int img_oob = p.M / p.HW_out + 1;                       // first image index past the tensor: the TMA unit zero-fills
+        const int col_oob = p.taps_total * p.b_cols_per_tap + IG_BLOCK_K;   // first weight column past the filter (+ a box)
         // tap -> offset inside the (padded) input window
         auto tap_offset = [&](int rr_, int sx_, int& cw_, int& ch_) {
           cw_ = sx_ * p.dil - p.pad;
@@ -161,8 +163,8 @@ igemm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt)          // a tap past the filter: image index out of range -> zeros
                       tma_load_4d(a_dst + mt * S::A_TILE_BYTES + jt * sub_a, &tmap_a, &full_bar[s], 0, cw, h0[mt] + ch,
-                                  real ? img[mt] : 0x3fffffff);
-                    tma_load_2d(b_dst + jt * sub_b, &tmap_b, &full_bar[s], real ? tp * p.b_cols_per_tap : 0x3fffffff, c.n0);
+                                  real ? img[mt] : img_oob);
+                    tma_load_2d(b_dst + jt * sub_b, &tmap_b, &full_bar[s], real ? tp * p.b_cols_per_tap : col_oob, c.n0);
                   }
                 } else {
                   int cw, ch;

@@ -554,7 +554,7 @@ class _ConvAct(torch.autograd.Function):
             dxn = None
             if stride == 2 and k == 4 and pad == 1 and dil == 1 and Co % 4 == 0 and e.conv_supported(Ho, Wo, Co, 1):
                 # data gradient of conv(4, s2, p1) == ConvTranspose2d(4, s2, p1) with the same weight tensor
-                wp = conv_math.pack_convT_s2_weight(weight)
+                wp = e.convT_pack(weight.detach())                 # == conv_math.pack_convT_s2_weight, one launch
                 dxn = conv_math.convT_s2(dz, wp, lambda a, w: e.conv2d_nhwc_bias_act(a, w, None, False, 1, 1, 1))
             elif stride == 1 and dil == 1 and Co % 4 == 0 and e.conv_supported(xn.shape[1], xn.shape[2], Co, 1):
                 dxn = e.conv2d_nhwc(dz, e.weight_flip(_krsc(weight).contiguous()), None, 1, k - 1 - pad, 1)
@@ -681,7 +681,7 @@ class _ConvTransposeAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         xn = _nhwc(x)
-        wp = conv_math.pack_convT_s2_weight(weight)
+        wp = ext().convT_pack(weight.detach())                     # == conv_math.pack_convT_s2_weight, one launch
         b4 = bias.repeat(4) if bias is not None else None          # phase-major channels (ph, pw, co)
         e = ext()
         out = conv_math.convT_s2(xn, wp, lambda a, w: e.conv2d_nhwc_bias_act(a, w, b4, bool(act), 1, 1, 1))

@@ -53,6 +53,16 @@ def test_conv_bias_act_forward_backward(B, H, Ci, Co, k, s, p, d, act):
     assert rel_err(gx, rx) < 5e-3 and rel_err(gw, rw) < 5e-3 and rel_err(gb, rb) < 5e-3
 
 
+def test_convT_weight_pack_kernel_equals_python_packing():
+    from federated_pytorch_test_b200.ops import conv_math
+    torch.manual_seed(3)
+    for Ci, Co in ((96, 48), (12, 3), (8, 8)):
+        w = torch.randn(Ci, Co, 4, 4, device=DEV)
+        assert torch.equal(cuda_ops.ext().convT_pack(w), conv_math.pack_convT_s2_weight(w))
+        wt = torch.randn(Co, 4, 4, Ci, device=DEV).permute(3, 0, 1, 2)          # same logical shape, other strides
+        assert torch.equal(cuda_ops.ext().convT_pack(wt), conv_math.pack_convT_s2_weight(wt))
+
+
 # the five dilated stem convolutions of the CPC encoder as ONE launch writing the concatenated tensor (simple_models.py:455-460)
 @pytest.mark.parametrize("B,H,Ci,Co,dils", [(32, 32, 8, 8, (1, 2, 4, 8, 16)), (9, 32, 8, 8, (1, 2, 4, 8, 16)), (16, 32, 4, 12, (1, 3)),
                                              (8, 16, 16, 8, (1, 2, 4))])
