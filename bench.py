@@ -159,14 +159,15 @@ def _collective_table(coll, topo, eng, iters: int = 20, warm: int = 3):
         n = x.numel()
         z = coll.zeros_like_block(x, "z")
         row = {"block": ci, "floats": n, "bytes": 4 * n}
-        variants = [("fused", True, "auto")]
+        dflt = bool(getattr(coll, "default_multimem", True))      # multimem (NVLS) from 4 ranks on, P2P loads / stores between 2
+        variants = [("fused", dflt, "auto")]
         if Wd > 1:
-            variants += [("fused_p2p", False, "auto"), ("fused_oneshot", True, "0")]
+            variants += [("fused_p2p", False, "auto"), ("fused_nvls", True, "auto"), ("fused_oneshot", dflt, "0")]
         for label, mc, mode in variants:
             coll.use_multimem, coll.two_shot_mode = mc, mode
             row[label + "_us"] = timed(lambda: coll._launch(0, [x], None, z, 0.0))
             row[label + "_two_shot"] = bool(coll.last_two_shot)
-        coll.use_multimem, coll.two_shot_mode = True, "auto"
+        coll.use_multimem, coll.two_shot_mode = dflt, "auto"
         coll.read_record()
         if Wd > 1:
             xr, zr = x.clone(), z.clone()
@@ -174,12 +175,13 @@ def _collective_table(coll, topo, eng, iters: int = 20, warm: int = 3):
             raw = x.clone()
             row["nccl_allreduce_only_us"] = timed(lambda: dist.all_reduce(raw))
             f = 2.0 * (Wd - 1) / Wd * 4 * n / 1e3          # bytes -> GB/s with us: bus bandwidth convention of nccl-tests
-            for k in ("fused", "fused_p2p", "fused_oneshot", "nccl", "nccl_allreduce_only"):
+            for k in ("fused", "fused_p2p", "fused_nvls", "fused_oneshot", "nccl", "nccl_allreduce_only"):
                 row[k + "_busGBs"] = f / row[k + "_us"]
             row["fused_frac_of_900GBs"] = row["fused_busGBs"] / 900.0
             row["speedup_vs_nccl"] = row["nccl_us"] / row["fused_us"]
+            row["speedup_vs_bare_allreduce"] = row["nccl_allreduce_only_us"] / row["fused_us"]
         rows.append(row)
-    return {"world": Wd, "multicast_bound": heap_mc, "transport": getattr(getattr(coll, "heap", None), "transport", "n/a"),
+    return {"world": Wd, "multicast_bound": heap_mc, "fused_default": "nvls multimem" if getattr(coll, "default_multimem", True) else "p2p loads/stores", "transport": getattr(getattr(coll, "heap", None), "transport", "n/a"),
             "timing": "CUDA events around %d back-to-back launches after %d warm-up, max over ranks; no host read inside" % (iters, warm),
             "rows": rows}
 

@@ -28,6 +28,7 @@ A *task* (``api/*.py``) supplies models, data, loss, schedule and evaluation.
 from __future__ import annotations
 
 import math
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
@@ -87,8 +88,16 @@ class Replica:
             net.to(device)
             self.arenas[key] = FlatArena(net, device=device, allocator=allocator,
                                          channels_last_weights=channels_last_weights)
-        self.running_loss = 0.0
+        self._running = 0.0             # running loss of the last pass: a device scalar until somebody asks (no sync per round)
         self.extra: Dict = {}
+
+    @property
+    def running_loss(self) -> float:
+        return float(self._running) if self._running is not None else 0.0
+
+    @running_loss.setter
+    def running_loss(self, v) -> None:
+        self._running = v
 
     def set_trainable(self, visit: Visit) -> None:
         for key, net in self.nets.items():
@@ -145,6 +154,8 @@ class EngineConfig:
     be_verbose: bool = False
     diagnostics: str = "post"        # 'post' = reference (extra forward after the step, Q17) | 'pre' = reuse closure loss
     graphs: bool = False             # CUDA-graph the Adam minibatch step
+    deferred_rounds: bool = True     # enqueue the next round's first minibatch BEFORE reading the aggregation's record (FedAvg / FedProx
+                                     # on the fused collective; not with per-round evaluation, verbose logs or resume records)
     graph_closures: bool = True      # ... and (with graphs=True) the L-BFGS closure: one graph for gradient evaluations, one for probes
     max_minibatches: Optional[int] = None   # cap per round (benchmarks / smoke tests)
     aggregate_in_epoch_loop: bool = True    # reference: aggregation sits inside the epoch loop
@@ -179,6 +190,7 @@ class Engine:
         self.step_hook: Optional[Callable[["Engine"], None]] = None
         self.last_loss1: Optional[torch.Tensor] = None
         self.graph_replays = 0
+        self._pending_round = None
         self.graph_kernel_launches = 0
         self.aggregations_done = 0
         self._resume_pos: Optional[Dict] = None       # set by ckpt.load_resume: schedule position to re-enter at
@@ -305,24 +317,28 @@ class Engine:
             self._restore_visit_state()
             self._resume_pos = None
         rounds = [(nadmm, epoch) for nadmm in range(cfg.Nadmm) for epoch in range(cfg.Nepoch)]
-        for ri, (nadmm, epoch) in enumerate(rounds):
-            if ri < first_round:
-                continue
-            self.last_epoch = epoch
-            if cfg.reset_optimizer_each_epoch and epoch > 0:
-                self.optimizers = [self._make_optimizer(rep, visit) for rep in self.replicas]
-            task.on_epoch_start(epoch, self)
-            with nvtx_range("fedb200:steps"):
-                self._run_replicas(visit, nloop, epoch, N)
-            if self.stop_requested:
-                return
-            last_epoch_of_round = epoch == cfg.Nepoch - 1
-            if cfg.aggregate_in_epoch_loop or last_epoch_of_round:
-                self._aggregate(visit, nloop, nadmm, epoch if cfg.aggregate_in_epoch_loop else cfg.Nepoch - 1, N)
-                if cfg.resume_path:
-                    from ..utils import ckpt
+        try:
+            for ri, (nadmm, epoch) in enumerate(rounds):
+                if ri < first_round:
+                    continue
+                self.last_epoch = epoch
+                if cfg.reset_optimizer_each_epoch and epoch > 0:
+                    self.optimizers = [self._make_optimizer(rep, visit) for rep in self.replicas]
+                task.on_epoch_start(epoch, self)
+                with nvtx_range("fedb200:steps"):
+                    self._run_replicas(visit, nloop, epoch, N)
+                if self.stop_requested:
+                    return
+                last_epoch_of_round = epoch == cfg.Nepoch - 1
+                if cfg.aggregate_in_epoch_loop or last_epoch_of_round:
+                    self._aggregate(visit, nloop, nadmm, epoch if cfg.aggregate_in_epoch_loop else cfg.Nepoch - 1, N)
+                    if cfg.resume_path:
+                        from ..utils import ckpt
 
-                    ckpt.save_resume(cfg.resume_path, self, dict(nloop=nloop, visit=vi, round=ri + 1, nadmm=nadmm, epoch=epoch))
+                        ckpt.save_resume(cfg.resume_path, self, dict(nloop=nloop, visit=vi, round=ri + 1, nadmm=nadmm, epoch=epoch))
+        finally:
+            if self._pending_round is not None:      # the last round of the visit (or a stop request): nothing left to overlap with
+                self._finish_round()
 
     def _restore_visit_state(self) -> None:
         st = self._resume_state or {}
@@ -381,7 +397,7 @@ class Engine:
         for i in range(len(reps)):
             cur.wait_stream(self._stream_of(i))
         for i, rep in enumerate(reps):
-            rep.running_loss = float(running[i]) if running[i] is not None else 0.0
+            rep.running_loss = running[i]
 
     def _one_step(self, rep: Replica, opt, visit: Visit, batch, pen: Penalty, running, i: int, epoch: int, nloop: int, N: int):
         cfg, task = self.cfg, self.task
@@ -390,6 +406,8 @@ class Engine:
                 loss1 = self._graphed_step(rep, opt, visit, batch, pen)
             else:
                 loss1 = self._train_step(rep, opt, visit, batch, pen)
+        if self._pending_round is not None:
+            self._finish_round()          # the GPU already has this minibatch queued behind the aggregation
         running = loss1 if running is None else running + loss1
         self.last_loss1 = loss1
         self.images_seen += task.batch_size_of(batch)
@@ -408,11 +426,26 @@ class Engine:
             running = self._one_step(rep, opt, visit, batch, pen, running, i, epoch, nloop, N)
             if self.stop_requested:
                 break
-        rep.running_loss = float(running) if running is not None else 0.0
+        rep.running_loss = running
 
     def _aggregate(self, visit: Visit, nloop: int, nadmm: int, epoch: int, N: int) -> None:
+        """End of a round.  The aggregation is ONE kernel in stream order (write-back included), so the next minibatch can
+        be queued right behind it; what the host wants from it (residuals, non-finite count, time-out status) is a record in
+        pinned memory.  With ``deferred_rounds`` the record is read after the next minibatch has been enqueued instead of
+        draining the GPU first (measured: the step that contained the round boundary took 3.3 ms instead of 2.24 ms)."""
+        cfg = self.cfg
+        defer = (cfg.deferred_rounds and self.topo.device.type == "cuda" and not cfg.check_results and not cfg.be_verbose
+                 and not cfg.resume_path and os.environ.get("FEDB200_DEFERRED_ROUNDS", "1") != "0")
         with nvtx_range("fedb200:aggregate"), self.timers.phase("aggregate"):
-            metrics = self.strategy.aggregate(nadmm)
+            token = self.strategy.aggregate_begin(nadmm) if defer else ("done", self.strategy.aggregate(nadmm))
+        self._pending_round = (token, visit, nloop, nadmm, epoch, N)
+        if token[0] == "done":
+            self._finish_round()
+
+    def _finish_round(self) -> None:
+        token, visit, nloop, nadmm, epoch, N = self._pending_round
+        self._pending_round = None
+        metrics = self.strategy.aggregate_end(token)
         self.aggregations_done += 1
         ctx = {"nloop": nloop, "nadmm": nadmm, "epoch": epoch, "N": N, "rho_mean": self.strategy.rho_mean()}
         if metrics is not None and getattr(self.coll, "last_nonfinite", 0.0):

@@ -63,6 +63,15 @@ class Strategy:
     def aggregate(self, nadmm: int) -> Dict[str, float]:
         raise NotImplementedError
 
+    # Split form used by the engine's deferred rounds: ``begin`` enqueues the aggregation, ``end`` reads its record.  The
+    # default is synchronous (begin does everything); FedAvg / FedProx on the fused collective only LAUNCH in ``begin``, so
+    # the host can queue the next minibatches before it waits for the residuals.
+    def aggregate_begin(self, nadmm: int):
+        return ("done", self.aggregate(nadmm))
+
+    def aggregate_end(self, token) -> Dict[str, float]:
+        return token[1]
+
     def rho_mean(self) -> float:
         return float("nan")
 
@@ -88,6 +97,17 @@ class FedAvg(Strategy):
         dual_sq = self.coll.fedavg_(self.xs, self.z, write_back=True)
         return {"dual": math.sqrt(max(float(dual_sq), 0.0)) / self.N}
 
+    def aggregate_begin(self, nadmm: int):
+        if getattr(self.coll, "supports_async", False):
+            self.coll.launch_fedavg_(self.xs, self.z, True)
+            return ("pending", self.N)
+        return ("done", self.aggregate(nadmm))
+
+    def aggregate_end(self, token) -> Dict[str, float]:
+        if token[0] == "done":
+            return token[1]
+        return {"dual": math.sqrt(max(float(self.coll.read_record()[0]), 0.0)) / token[1]}
+
     def load_state(self, st: Dict[str, object]) -> None:
         self.z.copy_(st["z"].to(self.z.device))
 
@@ -109,6 +129,18 @@ class FedProx(Strategy):
         rho = float(self.rho[self.ci, 0])
         dual_sq, primal = self.coll.fedprox_(self.xs, self.z, rho)
         return {"dual": math.sqrt(max(float(dual_sq), 0.0)) / self.N, "primal": float(primal) / self.N}
+
+    def aggregate_begin(self, nadmm: int):
+        if getattr(self.coll, "supports_async", False):
+            self.coll.launch_fedprox_(self.xs, self.z, float(self.rho[self.ci, 0]))
+            return ("pending", self.N)
+        return ("done", self.aggregate(nadmm))
+
+    def aggregate_end(self, token) -> Dict[str, float]:
+        if token[0] == "done":
+            return token[1]
+        v = self.coll.read_record()
+        return {"dual": math.sqrt(max(float(v[0]), 0.0)) / token[1], "primal": float(v[1]) / token[1]}
 
     def state(self) -> Dict[str, object]:
         return {"z": self.z, "rho": self.rho}
@@ -206,3 +238,20 @@ class ADMM(Strategy):
         rho = float(self.rho[self.ci, 0])
         dual_sq, primal = self.coll.admm_(self.xs, self.ys, self.z, rho, self._rho_slot())
         return {"dual": math.sqrt(max(float(dual_sq), 0.0)) / self.N, "primal": float(primal) / self.N}
+
+    def aggregate_begin(self, nadmm: int):
+        if not getattr(self.coll, "supports_async", False):
+            return ("done", self.aggregate(nadmm))
+        if self.bb.enabled:                      # the Barzilai-Borwein bookkeeping keeps its own (host-mirrored) log
+            if nadmm == 0:
+                self.coll.bb_seed_(self.xs, self.x0)
+            elif nadmm % self.bb.period_T == 0:
+                self._bb_update(nadmm)
+        self.coll.launch_admm_(self.xs, self.ys, self.z, float(self.rho[self.ci, 0]), self._rho_slot())
+        return ("pending", self.N)
+
+    def aggregate_end(self, token) -> Dict[str, float]:
+        if token[0] == "done":
+            return token[1]
+        v = self.coll.read_record()
+        return {"dual": math.sqrt(max(float(v[0]), 0.0)) / token[1], "primal": float(v[1]) / token[1]}

@@ -149,10 +149,17 @@ class FusedCollective(TorchCollective):
         self.bb_scratch = torch.zeros(_BB_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
         self.bb_log = torch.zeros(8 * max(topo.K, 1), dtype=torch.float32, device=dev)
         self.sync = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._host_out = torch.zeros(self.out.numel(), dtype=torch.float32).pin_memory()
+        self._out_event = torch.cuda.Event()
+        self._out_pending = False
         self.ctrl = self.heap.alloc(_PAD_WORDS, dtype=torch.int32)
         self.ctrl_ptrs = list(self.heap.locate(self.ctrl)[0]["peer_ptrs"])
         self._aux: Dict[Tuple[int, str], torch.Tensor] = {}
-        self.use_multimem = os.environ.get("FEDB200_MULTIMEM", "1") != "0"
+        # in-switch reduction pays from 4 peers on; between 2 GPUs the P2P variant of the same kernel is faster (nothing to reduce
+        # in the switch: 58.5 vs 77.3 us at 18.9 MB, profiles/r2_collective.md).  FEDB200_MULTIMEM=0|1 forces either.
+        mm = os.environ.get("FEDB200_MULTIMEM", "auto")
+        self.default_multimem = (topo.world_size > 2) if mm == "auto" else (mm != "0")
+        self.use_multimem = self.default_multimem
         self.two_shot_mode = TWO_SHOT_MODE
         self.max_blocks = int(max_blocks)
         self.timeout_s = BARRIER_TIMEOUT_S if timeout_s is None else float(timeout_s)
@@ -254,10 +261,32 @@ class FusedCollective(TorchCollective):
                               self.timeout_s)
         self.launches += 1
         self.last_two_shot = bool(two)
+        # the round's record follows the kernel into pinned host memory on the same stream: the host can enqueue the next
+        # minibatches first and pick the record up later without draining the GPU (Engine: deferred rounds)
+        if not torch.cuda.is_current_stream_capturing():
+            self._host_out.copy_(self.out, non_blocking=True)
+            self._out_event.record()
+            self._out_pending = True
+
+    supports_async = True
+
+    def launch_fedavg_(self, xs, z, write_back: bool = True) -> None:
+        self._launch(0 if write_back else 1, xs, None, z, 0.0)
+
+    def launch_fedprox_(self, xs, z, rho: float) -> None:
+        self._launch(1, xs, None, z, rho)
+
+    def launch_admm_(self, xs, ys, z, rho: float, rho_dev=None) -> None:
+        self._launch(2, xs, ys, z, rho, rho_dev)
 
     def read_record(self) -> List[float]:
         """The ONE device->host read of a round: dual^2, primal, #non-finite, status, rho, epoch, two-shot flag."""
-        vals = self.out.tolist()
+        if self._out_pending:
+            self._out_event.synchronize()
+            self._out_pending = False
+            vals = self._host_out.tolist()
+        else:
+            vals = self.out.tolist()
         if vals[OUT_STATUS] != 0.0:
             raise CollectiveTimeout("fedb200: rank %d timed out (%.0f s) waiting for rank %d in aggregation %d"
                                     % (self.topo.rank, self.timeout_s, int(vals[OUT_STATUS]) - 100, int(vals[OUT_EPOCH])))
