@@ -127,7 +127,7 @@ std::vector<Tensor> bn_elu_fwd(Tensor y, Tensor stats, Tensor gamma, Tensor beta
 // Returns (dy, dres or undefined); accumulates into dgamma / dbeta when given.
 std::vector<Tensor> bn_elu_bwd(Tensor dout, c10::optional<Tensor> out, Tensor y, Tensor mean, Tensor invstd, Tensor gamma,
                                c10::optional<Tensor> beta, c10::optional<Tensor> dgamma, c10::optional<Tensor> dbeta,
-                               bool want_dres, bool act) {
+                               bool want_dres, bool act, c10::optional<Tensor> sums_buf) {
   CHECK_F32_CUDA(dout); CHECK_CONTIG(dout); CHECK_CONTIG(y);
   c10::cuda::CUDAGuard guard(y.device());
   const int C = (int)y.size(-1);
@@ -135,21 +135,24 @@ std::vector<Tensor> bn_elu_bwd(Tensor dout, c10::optional<Tensor> out, Tensor y,
   const float* outp = nullptr;
   if (out.has_value() && out->defined()) { CHECK_CONTIG((*out)); outp = out->data_ptr<float>(); }
   const float* betap = opt_ptr(beta);
-  auto sums = torch::empty({2 * C}, y.options());
+  // sums_buf: a zeroed per-layer [2C + 1] buffer that the apply kernel leaves zeroed again (no memset node per layer)
+  static const bool fused_optin = [] { const char* e = std::getenv("FEDB200_BN_BWD_FUSED"); return e != nullptr && std::atoi(e) != 0; }();
+  const bool persistent = !fused_optin && sums_buf.has_value() && sums_buf->defined();   // the opt-in fused kernel zeroes its own scratch
+  if (persistent) TORCH_CHECK(sums_buf->numel() == 2 * C + 1 && sums_buf->is_contiguous(), "bn_elu_bwd: sums buffer must be [2C + 1]");
+  auto sums = persistent ? *sums_buf : torch::empty({2 * C + 1}, y.options());
   auto dy = torch::empty_like(y);
   Tensor dres;
   if (want_dres) dres = torch::empty_like(y);
   float* dg = (dgamma.has_value() && dgamma->defined()) ? dgamma->data_ptr<float>() : nullptr;
   float* db = (dbeta.has_value() && dbeta->defined()) ? dbeta->data_ptr<float>() : nullptr;
-  static const bool fused_optin = [] { const char* e = std::getenv("FEDB200_BN_BWD_FUSED"); return e != nullptr && std::atoi(e) != 0; }();
   if (fused_optin && fb::bn_elu_bwd_fused(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums),
                                           fptr_mut(dy), want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0,
                                           cur_stream()))
     return {dy, dres};
   fb::bn_elu_bwd_reduce(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums), M, C,
-                        act ? 1 : 0, cur_stream());
-  fb::bn_elu_bwd_apply(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr(sums), fptr_mut(dy),
-                       want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0, cur_stream());
+                        act ? 1 : 0, persistent ? 1 : 0, cur_stream());
+  fb::bn_elu_bwd_apply(fptr(dout), outp, fptr(y), fptr(mean), fptr(invstd), fptr(gamma), betap, fptr_mut(sums), fptr_mut(dy),
+                       want_dres ? dres.data_ptr<float>() : nullptr, dg, db, M, C, act ? 1 : 0, persistent ? 1 : 0, cur_stream());
   return {dy, dres};
 }
 // fused classifier head (experimental): x [N,H,W,C], w [O,C], bias [O] -> (logits [N,O], pooled [N,C])

@@ -8,6 +8,8 @@
 //  * avgpool_nhwc (+bwd), weight_krsc_flip (dgrad weights: swap Cin/Cout, rotate taps by 180 degrees)
 #include "fedb200.h"
 
+#include <cstdlib>
+
 #include <cooperative_groups.h>
 #include <stdexcept>
 #include <string>
@@ -133,8 +135,20 @@ __device__ __forceinline__ void block_quad_reduce(const float (&s1)[4], const fl
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
   }
 }
+static int reduce_rows_per_thread() {
+  static int rows = -1;
+  if (rows < 0) {
+    const char* v = std::getenv("FEDB200_RED_ROWS");
+    rows = (v != nullptr && std::atoi(v) > 0) ? std::atoi(v) : 4;
+  }
+  return rows;
+}
 static int reduce_grid(int M, int rpi) {
-  int grid = (M + rpi * 16 - 1) / (rpi * 16);     // >= 16 rows per thread: few blocks => few same-line reductions
+  // One block of four rows in flight per thread, at most two CTAs per SM.  The first version asked for >= 16 rows per thread (few
+  // blocks => few same-line atomics), which left the small tensors on 32-64 CTAs: 8.4 MB of layer4 activations in 14 us
+  // (profiles/r2_ncu_summary.md: `bn_elu_bwd_reduce_kernel<2>` grid 32, 7 % of the DRAM throughput).  FEDB200_RED_ROWS=16: old grid.
+  const int rows = reduce_rows_per_thread();
+  int grid = (M + rpi * rows - 1) / (rpi * rows);
   if (grid > sm_count() * 2) grid = sm_count() * 2;
   return grid < 1 ? 1 : grid;
 }
@@ -343,9 +357,9 @@ static int bwd_mode(const float* out, const float* beta, int act) {
   return 2;
 }
 void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                       const float* gamma, const float* beta, float* sums, int M, int C, int act, cudaStream_t s) {
+                       const float* gamma, const float* beta, float* sums, int M, int C, int act, int sums_clean, cudaStream_t s) {
   if ((C & 3) || C > 2 * RED_THREADS) throw std::runtime_error("fedb200: bn_elu_bwd needs C % 4 == 0 and C <= 1024");
-  cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s);
+  if (!sums_clean) cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s);     // a self-cleaning per-layer buffer arrives zeroed
   const int rpi = RED_THREADS / (C >> 2);
   const int grid = reduce_grid(M, rpi);
   const size_t smem = 2 * RED_THREADS * 4 * sizeof(float);
@@ -364,15 +378,17 @@ template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_elu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ sums,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float* sums,
                         float* __restrict__ dy, float* __restrict__ dres, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, int M, int C) {
+                        float* __restrict__ dbeta, int M, int C, int self_clean) {
   pdl_prologue();
+  __shared__ int s_last;
   const RowLayout L = row_layout(C, EW_THREADS);
-  if (L.r0 >= L.rpi) return;
-  const BnBwdCoef k = bn_bwd_coef(mean, invstd, gamma, beta, L.cq);
+  const bool active = L.r0 < L.rpi;
+  BnBwdCoef k;
   float ca[4], cb[4], cc[4];                      // dy = ca*du + cb*y + cc  (affine in du, y)
-  {
+  if (active) {
+    k = bn_bwd_coef(mean, invstd, gamma, beta, L.cq);
     const float invM = 1.f / float(M);
     const float4 a = reinterpret_cast<const float4*>(sums)[L.cq], b = reinterpret_cast<const float4*>(sums + C)[L.cq];
     const float4 g = reinterpret_cast<const float4*>(gamma)[L.cq];
@@ -389,6 +405,22 @@ bn_elu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
       }
     }
   }
+  if (self_clean) {
+    // `sums` = [sum du | sum du*xhat | counter] is a per-layer buffer that stays allocated: the last CTA to have read it
+    // re-zeroes it for the next backward pass (no memset node per BatchNorm layer in the captured step).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int t = atomicAdd(reinterpret_cast<unsigned int*>(sums + 2 * C), 1u);
+      s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sums[c] = 0.f;
+      if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(sums + 2 * C) = 0u;
+    }
+  }
+  if (!active) return;
   const int step = gridDim.x * L.rpi;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   auto emit = [&](size_t row, float4 d, float4 v) {
@@ -413,15 +445,15 @@ bn_elu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
   }
 }
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                      const float* gamma, const float* beta, const float* sums, float* dy, float* dres, float* dgamma,
-                      float* dbeta, int M, int C, int act, cudaStream_t s) {
+                      const float* gamma, const float* beta, float* sums, float* dy, float* dres, float* dgamma,
+                      float* dbeta, int M, int C, int act, int self_clean, cudaStream_t s) {
   if ((C & 3) || C > 4 * EW_THREADS) throw std::runtime_error("fedb200: bn_elu_bwd needs C % 4 == 0 and C <= 1024");
   const int rpi = EW_THREADS / (C >> 2);
   const int grid = stream_grid(M, rpi);
   switch (bwd_mode(out, beta, act)) {
-    case 0: launch_pdl(bn_elu_bwd_apply_kernel<0>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
-    case 1: launch_pdl(bn_elu_bwd_apply_kernel<1>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
-    default: launch_pdl(bn_elu_bwd_apply_kernel<2>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C); break;
+    case 0: launch_pdl(bn_elu_bwd_apply_kernel<0>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C, self_clean); break;
+    case 1: launch_pdl(bn_elu_bwd_apply_kernel<1>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C, self_clean); break;
+    default: launch_pdl(bn_elu_bwd_apply_kernel<2>, dim3(grid), dim3(EW_THREADS), 0, s, dout, out, y, mean, invstd, gamma, beta, sums, dy, dres, dgamma, dbeta, M, C, self_clean); break;
   }
   check_launch("bn_elu_bwd_apply");
 }

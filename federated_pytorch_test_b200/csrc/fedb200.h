@@ -100,10 +100,10 @@ void bn_elu_fwd(const float* y, float* stats, const float* gamma, const float* b
                 float eps, float momentum, int act, int self_clean, cudaStream_t s);
 // out == nullptr (allowed when the layer had no residual input): ELU' is recomputed from y, gamma, beta
 void bn_elu_bwd_reduce(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                       const float* gamma, const float* beta, float* sums, int M, int C, int act, cudaStream_t s);
+                       const float* gamma, const float* beta, float* sums, int M, int C, int act, int sums_clean, cudaStream_t s);
 void bn_elu_bwd_apply(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
-                      const float* gamma, const float* beta, const float* sums, float* dy, float* dres, float* dgamma,
-                      float* dbeta, int M, int C, int act, cudaStream_t s);
+                      const float* gamma, const float* beta, float* sums, float* dy, float* dres, float* dgamma,
+                      float* dbeta, int M, int C, int act, int self_clean, cudaStream_t s);
 // experimental single-kernel backward for small tensors (returns false when not applicable; sums: [2C] scratch)
 bool bn_elu_bwd_fused(const float* dout, const float* out, const float* y, const float* mean, const float* invstd,
                       const float* gamma, const float* beta, float* sums, float* dy, float* dres, float* dgamma,

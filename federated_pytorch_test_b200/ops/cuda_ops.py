@@ -176,6 +176,20 @@ def _stats_buffer(weight: torch.Tensor, C: int):
     return buf, True
 
 
+def _bwd_sums_buffer(gamma: torch.Tensor, C: int):
+    """Per-layer scratch of the BatchNorm backward ``[sum du | sum du*xhat | counter]``: zeroed once at allocation and left zeroed
+    again by ``bn_elu_bwd_apply`` (its last block), so the captured step has no memset node per BatchNorm layer.  ``None`` while a
+    graph is being captured before the buffer exists (graph-pool memory must not be cached): the binding then memsets a temporary."""
+    key = ("bwd", gamma.data_ptr(), C)
+    buf = _STATS_BUFFERS.get(key)
+    if buf is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        buf = torch.zeros(2 * C + 1, dtype=torch.float32, device=gamma.device)
+        _STATS_BUFFERS[key] = buf
+    return buf
+
+
 def clear_caches() -> None:
     """Derived tensors must follow their source weights (call after loading a checkpoint into existing parameters).
     Cached entries are refreshed IN PLACE: captured CUDA graphs hold their addresses."""
@@ -368,7 +382,7 @@ class _ConvBnAct(torch.autograd.Function):
         dbeta = torch.zeros_like(gamma) if need_b else None
         # without a residual input ELU' is recomputed from y (one tensor read less per backward pass)
         dy, dres = e.bn_elu_bwd(dn, out if (has_res or not act) else None, y, mean, invstd, gamma, beta, dgamma, dbeta,
-                                bool(has_res and need_r), act)
+                                bool(has_res and need_r), act, _bwd_sums_buffer(gamma, gamma.numel()))
         dx = dw = None
         kh, kw = wshape[2], wshape[3]
         if need_x:
@@ -434,7 +448,8 @@ class _ConvBnActSkip(torch.autograd.Function):
         need_x, need_w, need_g, need_b = ctx.needs_input_grad[:4]
         dgamma = torch.zeros_like(gamma) if need_g else None
         dbeta = torch.zeros_like(gamma) if need_b else None
-        dy, _ = e.bn_elu_bwd(_nhwc(dout), None, y, mean, invstd, gamma, beta, dgamma, dbeta, False, True)
+        dy, _ = e.bn_elu_bwd(_nhwc(dout), None, y, mean, invstd, gamma, beta, dgamma, dbeta, False, True,
+                             _bwd_sums_buffer(gamma, gamma.numel()))
         kh = wshape[2]
         dx = dw = None
         if need_x:

@@ -114,7 +114,7 @@ def test_fused_bn_backward_equals_two_pass_oracle(C, M, res, act):
     mean = y.mean(0)
     invstd = torch.rsqrt(y.var(0, unbiased=False) + 1e-5)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    dy, dres = e.bn_elu_bwd(dout, o.detach() if (res or not act) else None, y, mean, invstd, gamma, beta, dg, db, res, act)
+    dy, dres = e.bn_elu_bwd(dout, o.detach() if (res or not act) else None, y, mean, invstd, gamma, beta, dg, db, res, act, None)
     torch.testing.assert_close(dy, yr.grad, rtol=2e-3, atol=2e-4)
     torch.testing.assert_close(dg, gr.grad, rtol=2e-3, atol=2e-2)
     torch.testing.assert_close(db, br.grad, rtol=2e-3, atol=2e-2)

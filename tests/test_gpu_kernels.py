@@ -242,15 +242,21 @@ def test_bn_elu_forward_backward(C, M, res, act):
     torch.testing.assert_close(rv, rv2, rtol=1e-4, atol=1e-5)
     o.backward(dout)
     dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    dy, dres = e.bn_elu_bwd(dout, out, y, mean, invstd, gamma, beta, dg, db, res, act)
+    dy, dres = e.bn_elu_bwd(dout, out, y, mean, invstd, gamma, beta, dg, db, res, act, None)
     torch.testing.assert_close(dy, yr.grad, rtol=2e-3, atol=2e-4)
     if not res and act:   # ELU' recomputed from y instead of read from the layer output
-        dy2, _ = e.bn_elu_bwd(dout, None, y, mean, invstd, gamma, beta, None, None, False, act)
+        dy2, _ = e.bn_elu_bwd(dout, None, y, mean, invstd, gamma, beta, None, None, False, act, None)
         torch.testing.assert_close(dy2, yr.grad, rtol=2e-3, atol=2e-4)
     torch.testing.assert_close(dg, gr.grad, rtol=2e-3, atol=2e-2)
     torch.testing.assert_close(db, br.grad, rtol=2e-3, atol=2e-2)
     if res:
         torch.testing.assert_close(dres, rr.grad, rtol=1e-4, atol=1e-5)
+    # self-cleaning per-layer scratch [sum du | sum du*xhat | counter]: three calls on the same buffer, no memset between them
+    sb = torch.zeros(2 * C + 1, device=DEV)
+    for _ in range(3):
+        dy3, _ = e.bn_elu_bwd(dout, out, y, mean, invstd, gamma, beta, None, None, False, act, sb)
+        torch.testing.assert_close(dy3, dy, rtol=1e-5, atol=1e-6)
+    assert float(sb.abs().max()) == 0.0
 
 
 def _block_pair(cin, planes, stride):

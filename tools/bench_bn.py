@@ -35,7 +35,8 @@ def main():
         out, mean, invstd = e.bn_elu_fwd(y, stats, gamma, beta, res, rm, rv, 1e-5, 0.1, True, False)
         dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
         for label, o, want_res, tensors in (("bwd recompute", None, False, 5), ("bwd", out, False, 7), ("bwd+dres", out, True, 8)):
-            us = timed(lambda: e.bn_elu_bwd(dout, o, y, mean, invstd, gamma, beta, dg, db, want_res, True))
+            sb = torch.zeros(2 * C + 1, device=dev)      # self-cleaning per-layer scratch (no memset per call)
+            us = timed(lambda: e.bn_elu_bwd(dout, o, y, mean, invstd, gamma, beta, dg, db, want_res, True, sb))
             print("%-7s %-14s %7.1f us  %6.2f TB/s" % (name, label, us, tensors * mb / us), flush=True)
         st2 = torch.zeros(2 * C, device=dev)
         us = timed(lambda: e.col_stats(y, st2))
