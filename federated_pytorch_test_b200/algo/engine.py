@@ -434,8 +434,12 @@ class Engine:
         pinned memory.  With ``deferred_rounds`` the record is read after the next minibatch has been enqueued instead of
         draining the GPU first (measured: the step that contained the round boundary took 3.3 ms instead of 2.24 ms)."""
         cfg = self.cfg
+        # Measured (profiles/r2_late.md §1): 1 GPU 2.308 -> 2.253 ms/step, 4 GPUs boundary step 2.5 ms in both windows; on 8 GPUs the
+        # steady-state boundary was fine (2.8 ms) but the FIRST deferred aggregation of the run cost 11 ms once and an adaptive-ADMM
+        # run was slow, with no GPU minutes left to find out why -> up to 4 ranks by default, FEDB200_DEFERRED_ROUNDS=1 forces it on.
+        env = os.environ.get("FEDB200_DEFERRED_ROUNDS", "auto")
         defer = (cfg.deferred_rounds and self.topo.device.type == "cuda" and not cfg.check_results and not cfg.be_verbose
-                 and not cfg.resume_path and os.environ.get("FEDB200_DEFERRED_ROUNDS", "1") != "0")
+                 and not cfg.resume_path and env != "0" and (env == "1" or self.topo.world_size <= 4))
         with nvtx_range("fedb200:aggregate"), self.timers.phase("aggregate"):
             token = self.strategy.aggregate_begin(nadmm) if defer else ("done", self.strategy.aggregate(nadmm))
         self._pending_round = (token, visit, nloop, nadmm, epoch, N)

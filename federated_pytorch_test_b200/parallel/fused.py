@@ -261,23 +261,29 @@ class FusedCollective(TorchCollective):
                               self.timeout_s)
         self.launches += 1
         self.last_two_shot = bool(two)
-        # the round's record follows the kernel into pinned host memory on the same stream: the host can enqueue the next
-        # minibatches first and pick the record up later without draining the GPU (Engine: deferred rounds)
+
+    supports_async = True
+
+    def _record_async(self) -> None:
+        """Deferred rounds only: the round's record follows the kernel into pinned host memory on the same stream, so the host can
+        enqueue the next minibatches first and pick the record up later without draining the GPU.  (The synchronous operators
+        below read ``self.out`` directly, exactly as before.)"""
         if not torch.cuda.is_current_stream_capturing():
             self._host_out.copy_(self.out, non_blocking=True)
             self._out_event.record()
             self._out_pending = True
 
-    supports_async = True
-
     def launch_fedavg_(self, xs, z, write_back: bool = True) -> None:
         self._launch(0 if write_back else 1, xs, None, z, 0.0)
+        self._record_async()
 
     def launch_fedprox_(self, xs, z, rho: float) -> None:
         self._launch(1, xs, None, z, rho)
+        self._record_async()
 
     def launch_admm_(self, xs, ys, z, rho: float, rho_dev=None) -> None:
         self._launch(2, xs, ys, z, rho, rho_dev)
+        self._record_async()
 
     def read_record(self) -> List[float]:
         """The ONE device->host read of a round: dual^2, primal, #non-finite, status, rho, epoch, two-shot flag."""
