@@ -18,7 +18,9 @@ declare -A KERNELS=(
   [adam_prox]='_ZN7fedb20016adam_prox_kernelEPfPKfS0_S0_PKiiffffS2_S2_fffS2_'
   [bn_elu_fwd]='_ZN7fedb20017bn_elu_fwd_kernelEPKfPfS1_S1_S1_S2_S2_S2_S2_S2_iiffii'
   [bn_elu_bwd_reduce_1]='_ZN7fedb20024bn_elu_bwd_reduce_kernelILi1EEEvPKfS2_S2_S2_S2_S2_S2_Pfii'
-  [bn_elu_bwd_apply_1]='_ZN7fedb20023bn_elu_bwd_apply_kernelILi1EEEvPKfS2_S2_S2_S2_S2_S2_S2_PfS3_S3_S3_ii'
+  [bn_elu_bwd_apply_1]='_ZN7fedb20023bn_elu_bwd_apply_kernelILi1EEEvPKfS2_S2_S2_S2_S2_S2_PfS3_S3_S3_S3_iii'
+  [convT_pack]='_ZN7fedb20017convT_pack_kernelEPKfPfiixxxx'
+  [igemm_persistent_32x4x2x1]='_ZN7fedb20023igemm_persistent_kernelILi32ELi4ELi2ELi1EEEv14CUtensorMap_stS1_S1_NS_11IgemmParamsE'
   [gemm_f32]='_ZN7fedb20015gemm_f32_kernelILi32ELi32EEEvPKfS2_S2_Pfiiixxxxiii'
   [info_nce_fwd]='_ZN7fedb20019info_nce_fwd_kernelEPKfS1_iiPfS2_S2_'
 )
