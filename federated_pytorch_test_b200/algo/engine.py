@@ -438,7 +438,8 @@ class Engine:
         # steady-state boundary was fine (2.8 ms) but the FIRST deferred aggregation of the run cost 11 ms once and an adaptive-ADMM
         # run was slow, with no GPU minutes left to find out why -> up to 4 ranks by default, FEDB200_DEFERRED_ROUNDS=1 forces it on.
         env = os.environ.get("FEDB200_DEFERRED_ROUNDS", "auto")
-        defer = (cfg.deferred_rounds and self.topo.device.type == "cuda" and not cfg.check_results and not cfg.be_verbose
+        # (only a collective with asynchronous entry points actually defers: FusedCollective; the others answer "done")
+        defer = (cfg.deferred_rounds and not cfg.check_results and not cfg.be_verbose
                  and not cfg.resume_path and env != "0" and (env == "1" or self.topo.world_size <= 4))
         with nvtx_range("fedb200:aggregate"), self.timers.phase("aggregate"):
             token = self.strategy.aggregate_begin(nadmm) if defer else ("done", self.strategy.aggregate(nadmm))

@@ -126,3 +126,31 @@ def test_dilated_stem_and_tiny_map_conv_cpu_fallback():
     xp = F.pad(xc, (p, p, p, p))
     rows = xp.unfold(2, k, 1).unfold(3, k, 1).permute(0, 2, 3, 1, 4, 5).reshape(3 * 25, 5 * 4)
     assert torch.equal(rows, F.unfold(xc, (k, k), padding=p).transpose(1, 2).reshape(3 * 25, 20))
+
+
+def test_engine_deferred_rounds_same_trace_as_synchronous(monkeypatch):
+    """The engine's deferred-round protocol end to end (CPU, a collective with the asynchronous entry points of FusedCollective):
+    the record of a round is read after the next minibatch has been queued, the last round of a visit is finished at the visit's
+    end — same log lines in the same order, same parameters as the synchronous engine."""
+    from federated_pytorch_test_b200.api import common, federated_multi, fedprox_multi
+
+    tiny = dict(train_size=1024, test_size=128, save_model=False, graphs=False, fast=False, use_cuda=False, check_results=False)
+    for mod in (federated_multi, fedprox_multi):
+        traces = []
+        for cls in (TorchCollective, _AsyncCollective):
+            made = []
+
+            def make(topo, kind, _cls=cls):
+                made.append(_cls(topo))
+                return made[-1]
+
+            monkeypatch.setattr(common, "make_collective", make)
+            lines = []
+            eng = mod.run(mod.Config(K=3, Nloop=1, Nadmm=3, max_minibatches=2, **tiny), log=lines.append)
+            assert eng._pending_round is None
+            if cls is _AsyncCollective:
+                assert made[0].reads == eng.aggregations_done == 5 * 3
+            traces.append(([l for l in lines if l.startswith(("dual (", "block=["))], eng.replicas[1].arenas["net"].data.clone()))
+        (la, xa), (lb, xb) = traces
+        assert len(la) == 15 and la == lb
+        torch.testing.assert_close(xa, xb)
