@@ -111,3 +111,76 @@ def convT_s2(x_nhwc: torch.Tensor, w_packed: torch.Tensor, conv3x3: Callable[[to
 
 def conv3x3_oracle(x_nhwc: torch.Tensor, w_krsc: torch.Tensor) -> torch.Tensor:
     return F.conv2d(x_nhwc.permute(0, 3, 1, 2), w_krsc.permute(0, 3, 1, 2), None, 1, 1).permute(0, 2, 3, 1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Multi-dilation convolution (the CPC encoder stem, SURVEY G6, /root/reference/src/simple_models.py:441-460): B convolutions of
+# the SAME input with the same k x k / stride, their own dilation d_b / padding p_b and their own output channels, followed by a
+# channel concatenation, as ONE implicit GEMM:
+#     y[n, ho, wo, (b, co)] = sum_{r, s, ci} x[n, ho*stride + r*d_b - p_b, wo*stride + s*d_b - p_b, ci] * W_b[co, r, s, ci]
+# The kernel (csrc/igemm_persist_tcgen05.cuh, IgemmParams::ms_*) enumerates "filter rows" R = (b, r) of a merged filter
+# Wm[(b', co), (b, r), s, ci] = W_b[co, r, s, ci] if b' == b else 0 (block diagonal), and row R reads the input through branch
+# R // k's dilation and padding.  Everything below is plain PyTorch: the packing used by the GPU path and an oracle that gathers
+# the taps exactly in the kernel's order.
+# ------------------------------------------------------------------------------------------------
+def pack_multidil_weight(ws_oikk) -> torch.Tensor:
+    """B conv weights ``[Co, Ci, k, k]`` (same shape) -> merged KRSC filter ``[B*Co, B*k, k, Ci]`` (block diagonal)."""
+    B = len(ws_oikk)
+    Co, Ci, k, _ = ws_oikk[0].shape
+    w_all = torch.stack([w.permute(0, 2, 3, 1) for w in ws_oikk])                       # [B, Co, k, k, Ci]
+    wm = w_all.new_zeros(B, Co, B, k, k, Ci)
+    wm.diagonal(dim1=0, dim2=2).copy_(w_all.permute(1, 2, 3, 4, 0))                     # branch b -> rows (b, :) of its own channels
+    return wm.view(B * Co, B * k, k, Ci)
+
+
+def multidil_conv_oracle(x_nhwc: torch.Tensor, wm: torch.Tensor, k: int, stride: int, dils, pads) -> torch.Tensor:
+    """The kernel's tap enumeration in plain PyTorch: for filter row R = (b, r) and column s, one shifted / strided view of the
+    zero-padded input times the [C_out_total, C_in] slice of the merged filter."""
+    N, H, W, Ci = x_nhwc.shape
+    B = len(dils)
+    Ho = (H + 2 * pads[0] - dils[0] * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pads[0] - dils[0] * (k - 1) - 1) // stride + 1
+    big = max(max(pads), max(d * (k - 1) for d in dils))                                  # enough zero border for every tap
+    xp = F.pad(x_nhwc, (0, 0, big, big + stride, big, big + stride))
+    y = x_nhwc.new_zeros(N, Ho, Wo, wm.shape[0])
+    for R in range(B * k):
+        b, r = divmod(R, k)
+        d, p = dils[b], pads[b]
+        for s in range(k):
+            h0, w0 = big + r * d - p, big + s * d - p
+            tap = xp[:, h0: h0 + (Ho - 1) * stride + 1: stride, w0: w0 + (Wo - 1) * stride + 1: stride, :]
+            y = y + tap @ wm[:, R, s, :].t()
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# Tap packing (IgemmParams::cw): with C_in <= 16 a 32-wide k-block of the implicit GEMM holds 32 / cw filter taps, each as its own
+# cw-channel sub-tile, instead of one tap whose channels are padded to 32 with zeros.  k-block kb, sub-tile j covers tap
+# t = kb * (32 / cw) + j (taps past kh*kw contribute zeros); the activation sub-tile holds channels [0, C_in) of that tap and
+# zeros above, the weight sub-tile is the cw columns of the [C_out, kh*kw*C_in] filter matrix starting at column t * C_in — when
+# C_in < cw those columns run into the NEXT tap's weights, which meet the zero channels of the activation sub-tile.
+# ------------------------------------------------------------------------------------------------
+def tap_packed_gemm_oracle(x_nhwc: torch.Tensor, w_krsc: torch.Tensor, stride: int, pad: int, cw: int) -> torch.Tensor:
+    """conv(x, w) evaluated k-block by k-block exactly as the tap-packed kernel feeds the tensor core."""
+    N, H, W, Ci = x_nhwc.shape
+    Co, kh, kw, _ = w_krsc.shape
+    assert Ci <= cw and 32 % cw == 0
+    tpk = 32 // cw
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    xp = F.pad(x_nhwc, (0, 0, pad, pad, pad, pad))
+    wmat = w_krsc.reshape(Co, kh * kw * Ci)
+    wmat = F.pad(wmat, (0, 32))                                                           # reads past the filter give zeros (TMA OOB fill)
+    taps = kh * kw
+    y = x_nhwc.new_zeros(N * Ho * Wo, Co)
+    for kb in range(-(-taps // tpk)):
+        a = x_nhwc.new_zeros(N * Ho * Wo, 32)
+        bmat = x_nhwc.new_zeros(Co, 32)
+        for j in range(tpk):
+            t = kb * tpk + j
+            if t < taps:
+                r, s = divmod(t, kw)
+                tap = xp[:, r: r + (Ho - 1) * stride + 1: stride, s: s + (Wo - 1) * stride + 1: stride, :]
+                a[:, j * cw: j * cw + Ci] = tap.reshape(-1, Ci)                           # channels >= C_in of the sub-tile stay zero
+                bmat[:, j * cw: (j + 1) * cw] = wmat[:, t * Ci: t * Ci + cw]              # may run into the next tap's columns
+        y = y + a @ bmat.t()
+    return y.view(N, Ho, Wo, Co)

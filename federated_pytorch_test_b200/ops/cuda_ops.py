@@ -629,13 +629,11 @@ class _DilatedStem(torch.autograd.Function):
         B = len(dils)
         ws = params[0::2]
         Co, Ci = ws[0].shape[0], ws[0].shape[1]
-        w_all = torch.stack([w.permute(0, 2, 3, 1) for w in ws])                 # [B, Co, k, k, Ci]
-        wm = torch.zeros(B, Co, B, k, k, Ci, dtype=torch.float32, device=x.device)
-        wm.diagonal(dim1=0, dim2=2).copy_(w_all.permute(1, 2, 3, 4, 0))          # branch b -> rows (b, :) of its own channels
+        wm = conv_math.pack_multidil_weight(ws)                                  # [B*Co, B*k, k, Ci], block diagonal (CPU-tested)
         bias = torch.cat([b for b in params[1::2]]) if has_bias else None
         Ho = _conv_out(xn.shape[1], k, st, pads[0], dils[0])
         Wo = _conv_out(xn.shape[2], k, st, pads[0], dils[0])
-        out = e.conv2d_nhwc_multidil(xn, wm.view(B * Co, B * k, k, Ci), bias, bool(act), k, st, list(dils), list(pads), Ho, Wo)
+        out = e.conv2d_nhwc_multidil(xn, wm, bias, bool(act), k, st, list(dils), list(pads), Ho, Wo)
         ctx.save_for_backward(xn, out)
         ctx.cfg = cfg
         ctx.params = params
