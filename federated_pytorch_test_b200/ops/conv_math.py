@@ -184,3 +184,29 @@ def tap_packed_gemm_oracle(x_nhwc: torch.Tensor, w_krsc: torch.Tensor, stride: i
                 bmat[:, j * cw: (j + 1) * cw] = wmat[:, t * Ci: t * Ci + cw]              # may run into the next tap's columns
         y = y + a @ bmat.t()
     return y.view(N, Ho, Wo, Co)
+
+
+# ------------------------------------------------------------------------------------------------
+# Shuffle store (csrc/gemm_tcgen05.cu: conv2d_nhwc_shuffle_tf32): the phase-packed stride-1 convolution of `dgrad_s2` does not write
+# [N, Ho, Wo, (ph, pw, ci)] and shuffle it afterwards; each 32-row x 32-column epilogue chunk (32 consecutive output pixels of the
+# packed convolution = 32 / Wo whole rows, 32 consecutive packed channels = one phase, channels ci0 .. ci0+31) is ONE bulk tensor
+# store through a 5-D tensor map over the result viewed as {ci, pw, wo, ph, n*Ho + ho} with box {32, 1, Wo, 1, 32 / Wo} at
+# coordinates (ci0, pw, 0, ph, row0 / Wo).  Plain-PyTorch model of exactly that addressing:
+# ------------------------------------------------------------------------------------------------
+def shuffle_store_oracle(y_packed: torch.Tensor) -> torch.Tensor:
+    """``[N, Ho, Wo, 4*Ci]`` (channels (ph, pw, ci)) -> ``[N, 2Ho, 2Wo, Ci]`` by 32 x 32 chunk stores with the kernel's coordinates."""
+    N, Ho, Wo, C4 = y_packed.shape
+    Ci = C4 // 4
+    assert Ci % 32 == 0 and 32 % Wo == 0, "a chunk must stay inside one phase and cover whole output rows"
+    out = y_packed.new_zeros(N, 2 * Ho, 2 * Wo, Ci)
+    view5 = out.view(N * Ho, 2, Wo, 2, Ci)                    # [n*Ho + ho, ph, wo, pw, ci]: the tensor map's dims, slowest first
+    rows = y_packed.reshape(N * Ho * Wo, C4)
+    for row0 in range(0, rows.shape[0], 32):
+        for pc in range(0, C4, 32):
+            phase, ci0 = divmod(pc, Ci)
+            ph, pw = phase >> 1, phase & 1
+            hon0 = row0 // Wo
+            nrow = min(32, rows.shape[0] - row0)               # the last chunk is clipped by the tensor map's bounds
+            chunk = rows[row0: row0 + nrow, pc: pc + 32].reshape(nrow // Wo, Wo, 32)
+            view5[hon0: hon0 + nrow // Wo, ph, :, pw, ci0: ci0 + 32] = chunk
+    return out

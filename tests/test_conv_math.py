@@ -62,3 +62,11 @@ def test_tap_packed_k_blocks_equal_the_convolution(Ci, cw, k, stride, pad):
     ref = F.conv2d(x, w, None, stride, pad)
     y = conv_math.tap_packed_gemm_oracle(x.permute(0, 2, 3, 1).contiguous(), w.permute(0, 2, 3, 1).contiguous(), stride, pad, cw)
     torch.testing.assert_close(y.permute(0, 3, 1, 2), ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("N,Ho,Wo,Ci", [(3, 16, 16, 64), (2, 8, 8, 128), (5, 4, 4, 32), (1, 2, 2, 64)])
+def test_shuffle_store_addressing_equals_pixel_shuffle(N, Ho, Wo, Ci):
+    g = torch.Generator().manual_seed(Ho + Ci)
+    y = torch.randn(N, Ho, Wo, 4 * Ci, generator=g)
+    ref = y.view(N, Ho, Wo, 2, 2, Ci).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * Ho, 2 * Wo, Ci)
+    assert torch.equal(conv_math.shuffle_store_oracle(y), ref)
